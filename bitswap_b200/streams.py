@@ -1,0 +1,82 @@
+"""Device-resident ANS stream sets (host-side handle of `bsw_streams`).
+
+One stream == one reference state list (cifar_compress.py:157-159): 32-bit
+words bottom-first plus a 64-bit head.  `StreamSet` holds B of them in HBM."""
+import ctypes
+
+import numpy as np
+
+from ._lib import lib, check
+
+
+class StreamSet:
+    def __init__(self, n_streams: int, capacity_words: int):
+        self._h = ctypes.c_void_p()
+        check(lib().bsw_streams_create(ctypes.byref(self._h), int(n_streams), int(capacity_words)))
+        self.n = int(n_streams)
+        self.capacity = int(lib().bsw_streams_capacity(self._h))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().bsw_streams_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- host <-> device --------------------------------------------------------------------
+    def fill(self, words, head):
+        """Every stream := (words, head) -- the reference seeds each experiment identically."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        check(lib().bsw_streams_fill(self._h, w.ctypes.data, w.size, ctypes.c_uint64(int(head))))
+
+    def import_lists(self, states, first=0):
+        """states: iterable of reference-style lists [w0, ..., w_{n-1}, head]."""
+        states = list(states)
+        offs = np.zeros(len(states) + 1, dtype=np.int64)
+        for i, st in enumerate(states):
+            offs[i + 1] = offs[i] + len(st) - 1
+        words = np.zeros(max(int(offs[-1]), 1), dtype=np.uint32)
+        heads = np.zeros(len(states), dtype=np.uint64)
+        for i, st in enumerate(states):
+            words[offs[i]:offs[i + 1]] = np.array(st[:-1], dtype=np.uint64).astype(np.uint32)
+            heads[i] = st[-1]
+        check(lib().bsw_streams_import(self._h, first, len(states), words.ctypes.data, offs.ctypes.data, heads.ctypes.data))
+
+    def sizes(self):
+        """(nwords int64[B], heads uint64[B], flags int32[B]) -- synchronises."""
+        n = np.zeros(self.n, dtype=np.int64)
+        h = np.zeros(self.n, dtype=np.uint64)
+        f = np.zeros(self.n, dtype=np.int32)
+        check(lib().bsw_streams_sizes(self._h, n.ctypes.data, h.ctypes.data, f.ctypes.data))
+        return n, h, f
+
+    def export(self, first=0, count=None):
+        """Packed export: (words uint32[sum], offsets int64[count+1], heads uint64[count], flags)."""
+        count = self.n - first if count is None else count
+        n, h, f = self.sizes()
+        n, h, f = n[first:first + count], h[first:first + count], f[first:first + count]
+        offs = np.zeros(count + 1, dtype=np.int64)
+        np.cumsum(n, out=offs[1:])
+        words = np.zeros(max(int(offs[-1]), 1), dtype=np.uint32)
+        check(lib().bsw_streams_export(self._h, first, count, words.ctypes.data, offs.ctypes.data))
+        return words[:int(offs[-1])], offs, h, f
+
+    def export_lists(self, first=0, count=None):
+        words, offs, heads, flags = self.export(first, count)
+        return [[int(v) for v in words[offs[i]:offs[i + 1]]] + [int(heads[i])] for i in range(len(heads))]
+
+    def raise_on_error(self):
+        """Maps per-stream status flags to the reference's exception types."""
+        _, _, f = self.sizes()
+        if (f == 1).any():
+            raise IndexError(f"pop from empty ANS stack (streams {np.nonzero(f == 1)[0][:8].tolist()})")   # cifar_compress.py:65
+        if (f == 2).any():
+            raise OverflowError(f"ANS word-stack capacity exhausted (streams {np.nonzero(f == 2)[0][:8].tolist()})")
+        if (f != 0).any():
+            raise AssertionError(f"ANS stream error flags {np.unique(f).tolist()}")

@@ -1,0 +1,216 @@
+/*
+ * bitswap_b200.h -- C ABI of the B200-native Bit-Swap hot path.
+ *
+ * The reference (fhkingma/bitswap @ dfe0bf7d) is pure Python and has no FFI: its
+ * "plugin interface" for this path is a handful of Python call signatures
+ * (SURVEY.md 8b).  Each entry point below names the reference call it replaces.
+ * Python binds these with ctypes (bitswap_b200/_lib.py); INTEGRATION.md shows the
+ * stub a maintainer of the reference would add to cifar_compress.py.
+ *
+ * Conventions
+ *   - every function returns a bsw_status (0 = ok); nothing throws across the ABI
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch
+ *     tensors); the library never frees them.  "host" pointers are ordinary memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); every
+ *     kernel is enqueued on it, no call synchronises unless it says so.
+ *   - an ANS stream == one reference state list: 32-bit words bottom-first plus a
+ *     64-bit head (cifar_compress.py:157-159).  B streams = B independent chains.
+ */
+#ifndef BITSWAP_B200_H
+#define BITSWAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    BSW_OK          = 0,
+    BSW_E_UNDERFLOW = 1,   /* reference: IndexError from x.pop(-2)          (cifar_compress.py:65)    */
+    BSW_E_OVERFLOW  = 2,   /* word stack capacity exhausted (reference lists grow without bound)      */
+    BSW_E_BADTABLE  = 3,   /* reference: AssertionError on the cdf table    (cifar_compress.py:45-46) */
+    BSW_E_INVALID   = 4,   /* bad argument                                                            */
+    BSW_E_CUDA      = 5    /* CUDA runtime error; see bsw_last_error()                                */
+} bsw_status;
+
+const char *bsw_last_error(void);
+int         bsw_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stream sets: B device-resident ANS states.
+ * Replaces: the Python list `state` (cifar_compress.py:157-159) -- create/import == building the
+ * list, export == reading it back / pickle.dump (cifar_compress.py:265-266).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bsw_streams bsw_streams;
+
+/* capacity_words is rounded up to a multiple of 32. */
+int bsw_streams_create(bsw_streams **out, int n_streams, int64_t capacity_words);
+int bsw_streams_destroy(bsw_streams *s);
+int bsw_streams_count(const bsw_streams *s);
+int64_t bsw_streams_capacity(const bsw_streams *s);
+
+/* Host import: stream (first+i) receives words_host[offsets[i] .. offsets[i+1]) and heads_host[i].
+ * Synchronous. */
+int bsw_streams_import(bsw_streams *s, int first, int count, const uint32_t *words_host,
+                       const int64_t *offsets_host, const uint64_t *heads_host);
+/* Every stream receives the same words/head (the reference seeds every experiment identically,
+ * cifar_compress.py:93,157).  Synchronous. */
+int bsw_streams_fill(bsw_streams *s, const uint32_t *words_host, int64_t nwords, uint64_t head);
+/* Word counts (list length - 1), heads and per-stream status flags (bsw_status values). Synchronous. */
+int bsw_streams_sizes(bsw_streams *s, int64_t *nwords_host, uint64_t *heads_host, int32_t *flags_host);
+/* Packed export: stream i's words go to words_host[offsets_host[i] ...). Synchronous. */
+int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t *words_host, const int64_t *offsets_host);
+/* Raw device views for device-resident pipelines (NCCL gathers, custom kernels). */
+int bsw_streams_device_ptrs(bsw_streams *s, uint32_t **words_dev, int32_t **nwords_dev, uint64_t **heads_dev,
+                            int32_t **flags_dev);
+/* Device-side: sum over streams of (nwords) -> *total_dev (int64), async on `stream`. */
+int bsw_streams_total_words(bsw_streams *s, int64_t *total_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1  ANS.__init__ (cifar_compress.py:13-46): float64 pmfs [L,S] -> integer tables.
+ *     P_dev [L,S] uint32, C_dev [L,S+1] uint32 (C[:,S] == 2^bits).  err_dev (int32, may be NULL) is
+ *     set to BSW_E_BADTABLE if a row fails the reference's assertions.
+ * ---------------------------------------------------------------------------------------------- */
+int bsw_ans_tables(const double *pmfs_dev, int64_t L, int S, int bits, int quantbits,
+                   uint32_t *P_dev, uint32_t *C_dev, int32_t *err_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a2/a3  ANS.encode / ANS.decode (cifar_compress.py:48-67) over given integer tables, batched over
+ *     the set's streams [first, first+count).  Tables: P [.,L,S], C [.,L,S+1]; table_stream_stride
+ *     = elements between consecutive streams' tables (0: one table shared by all streams).
+ *     Symbols: int32 [count, L].  push walks rows ascending, pop descending, exactly as the
+ *     reference loops do.
+ * ---------------------------------------------------------------------------------------------- */
+int bsw_ans_push(bsw_streams *s, int first, int count, const uint32_t *P_dev, const uint32_t *C_dev,
+                 int64_t P_stream_stride, int64_t C_stream_stride, const int32_t *sym_dev,
+                 int64_t L, int S, int bits, void *stream);
+int bsw_ans_pop(bsw_streams *s, int first, int count, const uint32_t *P_dev, const uint32_t *C_dev,
+                int64_t P_stream_stride, int64_t C_stream_stride, int32_t *sym_dev,
+                int64_t L, int S, int bits, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a4  logistic_cdf + pmf assembly (utils/torch/rand.py:67-68, cifar_compress.py:182-184).
+ *     endpoints_dev: row r starts at endpoints_dev + r*endp_row_stride and holds S-1 doubles
+ *     (stride 0 = one row shared by all, as ImageBins' identical rows allow).
+ *     mu/scale: double, indexed [r*ms] (ms = 0 broadcasts, as the prior does at :245).
+ *     Writes pmfs_dev [L,S] float64 -- the debug/export path of the parity ladder (P2); the hot
+ *     path never materialises pmfs.
+ * ---------------------------------------------------------------------------------------------- */
+int bsw_logistic_pmfs(const double *endpoints_dev, int64_t endp_row_stride, const double *mu_dev,
+                      const double *scale_dev, int64_t ms, int64_t L, int S, double *pmfs_dev, void *stream);
+
+/* a4+a1 fused, materialised: integer tables straight from (endpoints, mu, scale).  Used for tables
+ * that are shared by every stream (the Logistic(0,1) prior, cifar_compress.py:245-247). */
+int bsw_logistic_tables(const double *endpoints_dev, int64_t endp_row_stride, const double *mu_dev,
+                        const double *scale_dev, int64_t ms, int64_t L, int S, int bits, int quantbits,
+                        uint32_t *P_dev, uint32_t *C_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a4+a1+a2 / a4+a1+a3 fused hot kernels: one warp per stream builds each row's table in registers
+ * (float64 logistic cdf -> trunc -> remnant at the row argmax -> scan) and codes the symbol; tables
+ * never reach HBM.  Replaces the per-level sequence
+ *     cdfs = logistic_cdf(...); pmfs = ...; ANS(pmfs, bits, q).encode/decode(state, ...)
+ * of cifar_compress.py:182-187,197-202.
+ *     mu_dev/scale_dev: float32 (the nets' outputs, up-cast to float64 in the kernel as
+ *     model/cifar_train.py:375-376 does); element [b*mu_stream_stride + r].  A stream stride of 0
+ *     shares the vector between streams (the unconditional x-scale, cifar_train.py:411).
+ *     endpoints as above but each row holds S doubles, the last one +inf (library layout, see
+ *     bsw_bins_*).  S must be a multiple of 32 and <= 1024.
+ *     sym: int16 [count, L].
+ * ---------------------------------------------------------------------------------------------- */
+int bsw_logistic_push(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
+                      const float *scale_dev, int64_t scale_stream_stride, const double *endpoints_dev,
+                      int64_t endp_row_stride, const int16_t *sym_dev, int64_t L, int S, int bits,
+                      int quantbits, void *stream);
+int bsw_logistic_pop(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
+                     const float *scale_dev, int64_t scale_stream_stride, const double *endpoints_dev,
+                     int64_t endp_row_stride, int16_t *sym_dev, int64_t L, int S, int bits,
+                     int quantbits, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bin tables on the device.
+ * Replaces: the tensors returned by discretize() (discretization.py:9-99) and ImageBins
+ * (utils/torch/rand.py:134-153); the library keeps its own padded copy (each endpoint row padded
+ * with +inf to S entries so that cdf_{S-1} == 1 falls out of the same formula).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bsw_bins bsw_bins;
+/* zendpoints_host [nz, zdim, S-1], zcentres_host [nz, zdim, S] float64 (reference layout). */
+int bsw_bins_create(bsw_bins **out, int nz, int zdim, int quantbits, int xdim,
+                    const double *zendpoints_host, const double *zcentres_host);
+int bsw_bins_destroy(bsw_bins *b);
+/* Device views: padded z endpoints of a level [zdim, S]; z centres of a level [zdim, S]; the single
+ * padded x endpoint row [256]. */
+int bsw_bins_device_ptrs(bsw_bins *b, int level, const double **zend_dev, const double **zcen_dev,
+                         const double **xend_dev);
+
+/* a5  centre gathers (cifar_compress.py:180,195): symbols -> float32 values fed to the nets
+ *     (float64 table value cast to float32, model/cifar_train.py:324,392).
+ *     z: out[b,d] = (float) zcentres[level, d, sym[b,d]];  x: out[b,d] = (float)((x-127.5)/127.5). */
+int bsw_gather_zcentres(const bsw_bins *b, int level, const int16_t *sym_dev, float *out_dev, int64_t n_streams,
+                        void *stream);
+int bsw_gather_xcentres(const uint8_t *x_dev, float *out_dev, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a8-a10  The inference-time VAE.
+ * Replaces: Model.infer(i)(given) / Model.generate(i)(given) in compressing mode
+ * (model/cifar_train.py:315-438; imagenetcrop_train.py:306-315,417) and the WnConv2d / ResNetLayer /
+ * Squeeze2d / UnSqueeze2d forwards they run (utils/torch/modules.py:98-106,175-241).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bsw_model bsw_model;
+typedef struct {
+    int32_t xc;            /* image channels C (xs = (C,32,32)) */
+    int32_t nz;
+    int32_t zchannels;
+    int32_t nprocessing;
+    int32_t kernel_size;   /* 3 */
+    int32_t resdepth;
+    int32_t reswidth;
+    int32_t cond_xscale;   /* imagenetcrop: x-scale from a conv head */
+    int32_t max_batch;     /* activations are preallocated for this many images */
+    int32_t use_tensor_cores; /* 1: tcgen05 path for the W->W convs (needs padded width 256); 0: fp32 SIMT */
+} bsw_model_desc;
+
+int bsw_model_create(bsw_model **out, const bsw_model_desc *desc);
+int bsw_model_destroy(bsw_model *m);
+/* Loads one WnConv2d by its reference state_dict prefix (e.g. "infer_res0.0.res252layer1.conv1"):
+ * v [O,I,k,k], gain [O], b [O] float32 host arrays.  Weight normalisation
+ * w = v * g/(||v||+1e-10), g = softplus(gain) if loggain else gain (modules.py:98-105) is folded here,
+ * once.  Synchronous. */
+int bsw_model_load_conv(bsw_model *m, const char *prefix, const float *v_host, const float *gain_host,
+                        const float *b_host, int O, int I, int k, int loggain);
+/* The unconditional x-scale parameter gen_std [C,32,32] (model/cifar_train.py:306-308). */
+int bsw_model_load_gen_std(bsw_model *m, const float *gen_std_host);
+/* Call after all tensors are loaded; checks completeness. */
+int bsw_model_finalize(bsw_model *m);
+
+/* given_dev float32 [n, dim_in] flat CHW (what `given.float()` is in the reference);
+ * mu_dev/scale_dev float32 [n, dim_out] flat CHW.  For generate(0) without cond_xscale the scale does
+ * not depend on the input: scale_dev receives the [xdim] vector replicated n times only if
+ * scale_per_stream != 0, else one [xdim] row. */
+int bsw_vae_infer(bsw_model *m, int level, const float *given_dev, int64_t n, float *mu_dev, float *scale_dev,
+                  void *stream);
+int bsw_vae_generate(bsw_model *m, int level, const float *given_dev, int64_t n, float *mu_dev, float *scale_dev,
+                     int scale_per_stream, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a11/a12  The Bit-Swap recursion, device resident.
+ * Replaces: the sender loop body of cifar_compress.py:175-204,244-250 and the receiver loop body of
+ * :283-317 for `count` streams at once (one image per stream per call; chain images by calling again).
+ * x_dev uint8 [count, C,32,32].  No host round trip between levels; errors land in the per-stream
+ * flags (bsw_streams_sizes).  `scheme`: 0 = Bit-Swap, 1 = BB-ANS (cifar_compress.py:205-242,319-352).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bsw_codec bsw_codec;
+int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int max_batch);
+int bsw_codec_destroy(bsw_codec *c);
+int bsw_codec_encode(bsw_codec *c, bsw_streams *s, int first, int count, const uint8_t *x_dev, int scheme,
+                     void *stream);
+int bsw_codec_decode(bsw_codec *c, bsw_streams *s, int first, int count, uint8_t *x_dev, int scheme,
+                     void *stream);
+/* Number of kernel launches the last encode/decode call enqueued (bench.py's gpu_launches). */
+int64_t bsw_codec_last_launches(const bsw_codec *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BITSWAP_B200_H */

@@ -1,0 +1,275 @@
+"""GPU parity of the coder kernels against the oracle (through the C ABI, ctypes).
+
+Parity ladder:
+  P0  integer coder on injected integer tables      -> state lists bit-identical to the oracle
+  P1  table quantiser on injected float64 pmfs      -> P, C bit-identical to ANS.__init__
+  P2  float64 logistic pmfs                         -> == torch-CUDA's own sigmoid expression bit for bit,
+                                                       <= 4e-16 from the torch-CPU golden; and feeding OUR
+                                                       pmfs to the oracle coder reproduces OUR fused-kernel
+                                                       state bit for bit.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O                      # noqa: E402  (checker only)
+from bitswap_b200 import synthetic                   # noqa: E402
+from bitswap_b200._lib import lib, check, cuda_stream_ptr   # noqa: E402
+from bitswap_b200.ans import ANS                     # noqa: E402
+from bitswap_b200.streams import StreamSet           # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KATS = json.load(open(os.path.join(GOLDEN, "ans_kat.json")))
+dev = "cuda"
+
+
+def _kat_inputs(k):
+    rs = np.random.RandomState(k["seed"])
+    pm = rs.dirichlet(np.ones(k["S"]) * 0.5, size=k["L"])
+    sym = rs.randint(0, k["S"], size=k["L"])
+    w, head = synthetic.initial_words(k["N"], seed=100)
+    return pm, sym, [int(v) for v in w] + [head]
+
+
+@pytest.mark.parametrize("k", KATS, ids=[k["name"] for k in KATS])
+def test_kat_dropin_ans(k):
+    """The reference's own call sequence on the drop-in class reproduces the reference's states."""
+    pm, sym, st0 = _kat_inputs(k)
+    a = ANS(torch.from_numpy(pm).to(dev), 31, k["q"])
+    assert [int(v) for v in a.pmfs[0, :6]] == k["P_row0_head"]
+    pushed = a.encode(st0.copy(), torch.from_numpy(sym).to(dev))
+    assert (len(pushed), hex(pushed[-1])) == (k["push_len"], k["push_head"])
+    assert O.CState.from_list(pushed).digest() == k["push_sha"]
+    popped, psym = a.decode(st0.copy())
+    assert psym.dtype == torch.int64 and psym.device.type == "cuda"
+    assert (len(popped), hex(popped[-1])) == (k["pop_len"], k["pop_head"])
+    assert O.CState.from_list(popped).digest() == k["pop_sha"]
+    assert [int(v) for v in psym[:6].cpu()] == k["pop_syms_head"]
+    back, rsym = a.decode(pushed.copy())
+    assert back == st0 and np.array_equal(rsym.cpu().numpy(), sym)
+    assert a.encode(popped.copy(), psym) == st0
+
+
+def test_underflow_and_overflow_map_to_reference_exceptions():
+    k = KATS[1]
+    pm, sym, _ = _kat_inputs(k)
+    w, head = synthetic.initial_words(512, seed=100)
+    a = ANS(torch.from_numpy(pm).to(dev), 31, k["q"])
+    with pytest.raises(IndexError):
+        a.decode([int(v) for v in w] + [head])
+    # overflow: a stream set with too little capacity
+    ss = StreamSet(1, 32)
+    ss.fill(w[:20], head)
+    s32 = torch.from_numpy(sym.astype(np.int32)).to(dev)
+    check(lib().bsw_ans_push(ss.handle, 0, 1, a._P.data_ptr(), a._C.data_ptr(), 0, 0, s32.data_ptr(),
+                             a.seq_len, a.support, 31, cuda_stream_ptr()))
+    with pytest.raises(OverflowError):
+        ss.raise_on_error()
+
+
+def test_bad_arguments_are_rejected():
+    ss = StreamSet(2, 64)
+    rc = lib().bsw_ans_push(ss.handle, 1, 2, None, None, 0, 0, None, 4, 4, 31, None)
+    assert rc == 4 and b"range" in lib().bsw_last_error()
+
+
+@pytest.mark.parametrize("L,S,q", [(8, 16, 4), (12, 16, 4), (300, 100, 6), (512, 256, 8), (256, 1024, 10), (40, 3000, 10)])
+def test_p1_tables_bit_identical(L, S, q):
+    g = np.load(os.path.join(GOLDEN, "tables_small.npz"))
+    rs = np.random.RandomState(L + S)
+    if (L, S) == (12, 16):
+        pm, Pw, Cw = g["pm_a"], g["P_a"], g["C_a"]          # includes tied-argmax rows (reference tie rule)
+    else:
+        pm = rs.dirichlet(np.ones(S) * rs.choice([0.05, 0.5, 5.0]), size=L)
+        pm[0] = 1.0 / S                                       # exact tie across the whole row
+        Pw, Cw = O.tables_c(pm, 31, q)
+    a = ANS(torch.from_numpy(pm).to(dev), 31, q)
+    assert np.array_equal(a.pmfs, Pw) and np.array_equal(a.cdfs, Cw)
+
+
+@pytest.mark.parametrize("B,L,S,shared", [(37, 200, 16, False), (64, 333, 100, False), (33, 512, 256, True), (16, 700, 1024, False)])
+def test_p0_batched_coder_vs_oracle(B, L, S, shared):
+    """Injected integer tables + symbols + initial words: every stream's exported list == oracle's."""
+    rs = np.random.RandomState(B * 7 + S)
+    q = 4
+    T = 1 if shared else B
+    pm = rs.dirichlet(np.ones(S) * 0.3, size=(T, L))
+    tabs = [O.tables_c(pm[t], 31, q) for t in range(T)]
+    P = torch.from_numpy(np.stack([t[0] for t in tabs]).astype(np.uint32).view(np.int32)).to(dev)
+    C = torch.from_numpy(np.stack([t[1] for t in tabs]).astype(np.uint32).view(np.int32)).to(dev)
+    sym = rs.randint(0, S, size=(B, L)).astype(np.int32)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(400 + 13 * b, seed=100 + b)
+        states.append([int(v) for v in w] + [head])
+    ss = StreamSet(B, 4096)
+    ss.import_lists(states)
+    pss, css = (0, 0) if shared else (L * S, L * (S + 1))
+    dsym = torch.from_numpy(sym).to(dev)
+    # push, compare; then pop everything back, compare symbols and the restored state
+    check(lib().bsw_ans_push(ss.handle, 0, B, P.data_ptr(), C.data_ptr(), pss, css, dsym.data_ptr(), L, S, 31, cuda_stream_ptr()))
+    ss.raise_on_error()
+    got = ss.export_lists()
+    for b in range(B):
+        a = O.AnsC(tables=tabs[0 if shared else b])
+        want = a.encode(O.CState.from_list(states[b]), sym[b]).to_list()
+        assert got[b] == want, f"stream {b} differs after push"
+    out = torch.zeros((B, L), dtype=torch.int32, device=dev)
+    check(lib().bsw_ans_pop(ss.handle, 0, B, P.data_ptr(), C.data_ptr(), pss, css, out.data_ptr(), L, S, 31, cuda_stream_ptr()))
+    ss.raise_on_error()
+    assert np.array_equal(out.cpu().numpy(), sym)
+    assert ss.export_lists() == states
+    # pop-first (bits-back direction) on a sub-range of streams only
+    first, cnt = 3, B - 5
+    check(lib().bsw_ans_pop(ss.handle, first, cnt, P.data_ptr() + (0 if shared else first * L * S * 4),
+                            C.data_ptr() + (0 if shared else first * L * (S + 1) * 4), pss, css, out.data_ptr(), L, S, 31,
+                            cuda_stream_ptr()))
+    ss.raise_on_error()
+    got = ss.export_lists()
+    o = out.cpu().numpy()
+    for b in range(B):
+        if first <= b < first + cnt:
+            a = O.AnsC(tables=tabs[0 if shared else b])
+            st, s = a.decode(O.CState.from_list(states[b]))
+            assert got[b] == st.to_list() and np.array_equal(o[b - first], s)
+        else:
+            assert got[b] == states[b]
+
+
+def _ref_pmfs_cuda(ends, mu, sc):
+    """The reference's tensor expression (cifar_compress.py:182-184) evaluated by torch ON THE GPU, as the
+    reference itself runs it (device = cuda, cifar_compress.py:77)."""
+    cdfs = torch.sigmoid((ends.t() - mu) / sc).t()
+    pmfs = cdfs[:, 1:] - cdfs[:, :-1]
+    return torch.cat((cdfs[:, 0].unsqueeze(1), pmfs, 1. - cdfs[:, -1].unsqueeze(1)), dim=1)
+
+
+def test_p2_logistic_pmfs():
+    g = np.load(os.path.join(GOLDEN, "pmfs_small.npz"))
+    for ends, mu, sc, want in ((g["ends"], g["mu"], g["sc"], g["pm"]), (g["xe"], g["xmu"], g["xsc"], g["xpm"]),
+                               (g["ends"], np.zeros(1), np.ones(1), g["prior"])):
+        L, S = want.shape
+        e, m, s = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (ends, mu, sc))
+        out = torch.empty((L, S), dtype=torch.float64, device=dev)
+        check(lib().bsw_logistic_pmfs(e.data_ptr(), S - 1, m.data_ptr(), s.data_ptr(), 1 if m.numel() > 1 else 0, L, S,
+                                      out.data_ptr(), cuda_stream_ptr()))
+        assert np.abs(out.cpu().numpy() - want).max() <= 4e-16          # vs torch-CPU (reference classes) golden
+        assert torch.equal(out, _ref_pmfs_cuda(e, m, s))                  # vs the reference expression on this GPU
+    # a full-size level: 2048 x 1024, bit-exact against torch-CUDA
+    rs = np.random.RandomState(1)
+    L, S = 2048, 1024
+    lo, hi = -6 - rs.uniform(0, 1, L), 6 + rs.uniform(0, 1, L)
+    e = torch.from_numpy(np.linspace(lo, hi, S + 1, axis=1)[:, 1:-1].copy()).to(dev)
+    m = torch.from_numpy(rs.normal(0, 2, L).astype(np.float32)).double().to(dev)
+    s = torch.from_numpy(rs.uniform(0.1, 1.0, L).astype(np.float32)).double().to(dev)
+    out = torch.empty((L, S), dtype=torch.float64, device=dev)
+    check(lib().bsw_logistic_pmfs(e.data_ptr(), S - 1, m.data_ptr(), s.data_ptr(), 1, L, S, out.data_ptr(), cuda_stream_ptr()))
+    ref = _ref_pmfs_cuda(e, m, s)
+    assert torch.equal(out, ref), f"{(out != ref).sum().item()} of {out.numel()} pmfs differ from torch-CUDA"
+
+
+def _pad_inf(ends):
+    L, Sm1 = ends.shape
+    out = np.full((L, Sm1 + 1), np.inf)
+    out[:, :Sm1] = ends
+    return out
+
+
+@pytest.mark.parametrize("B,L,S,q,kind", [(9, 100, 64, 6, "z"), (20, 256, 128, 7, "z"), (33, 3072, 256, 8, "x"),
+                                         (17, 2048, 1024, 10, "z"), (5, 515, 512, 9, "z"), (6, 64, 32, 5, "z")])
+def test_p2_fused_logistic_coder_vs_oracle_on_our_pmfs(B, L, S, q, kind):
+    """Fused kernels (table in registers, reciprocal-division shortcut) vs: our exported float64 pmfs (true
+    division) -> oracle ANS.__init__ -> oracle coder.  Bit-identical states and symbols for every stream."""
+    rs = np.random.RandomState(B + L + S)
+    if kind == "x":      # ImageBins: one endpoint row shared by all dims, scale shared by all streams
+        from bitswap_b200.rand import ImageBins
+        ends = ImageBins(torch.float64, "cpu", 1).endpoints().numpy()          # [1, 255]
+        ends_rows = np.repeat(ends, L, axis=0)
+        mu = rs.uniform(-1, 1, (B, L)).astype(np.float32)
+        sc = np.repeat(rs.uniform(0.003, 0.7, (1, L)).astype(np.float32), B, axis=0)
+        ers, sss = 0, 0
+    else:
+        lo, hi = -6 - rs.uniform(0, 1, L), 6 + rs.uniform(0, 1, L)
+        ends_rows = np.linspace(lo, hi, S + 1, axis=1)[:, 1:-1].copy()
+        ends = ends_rows
+        mu = rs.normal(0, 2, (B, L)).astype(np.float32)
+        sc = rs.uniform(0.1, 1.0, (B, L)).astype(np.float32)
+        ers, sss = S, L
+    e_pad = torch.from_numpy(_pad_inf(ends)).to(dev)
+    e_raw = torch.from_numpy(np.ascontiguousarray(ends_rows)).to(dev)
+    dmu, dsc = torch.from_numpy(mu).to(dev), torch.from_numpy(sc).to(dev)
+    dsc_arg = dsc[:1].contiguous() if kind == "x" else dsc
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(1500 + 7 * b, seed=100 + b)
+        states.append([int(v) for v in w] + [head])
+    ss = StreamSet(B, 1 << 14)
+    ss.import_lists(states)
+    # oracle side, on OUR pmfs
+    tabs = []
+    for b in range(B):
+        pm = torch.empty((L, S), dtype=torch.float64, device=dev)
+        check(lib().bsw_logistic_pmfs(e_raw.data_ptr(), S - 1, dmu[b].double().contiguous().data_ptr(),
+                                      dsc[b].double().contiguous().data_ptr(), 1, L, S, pm.data_ptr(), cuda_stream_ptr()))
+        torch.cuda.synchronize()
+        tabs.append(O.tables_c(pm.cpu().numpy(), 31, q))
+    # pop first (bits-back), then push other symbols
+    out = torch.zeros((B, L), dtype=torch.int16, device=dev)
+    check(lib().bsw_logistic_pop(ss.handle, 0, B, dmu.data_ptr(), L, dsc_arg.data_ptr(), sss, e_pad.data_ptr(), ers,
+                                 out.data_ptr(), L, S, 31, q, cuda_stream_ptr()))
+    ss.raise_on_error()
+    got = ss.export_lists()
+    o = out.cpu().numpy()
+    ost = []
+    for b in range(B):
+        st, s = O.AnsC(tables=tabs[b]).decode(O.CState.from_list(states[b]))
+        assert np.array_equal(o[b], s), f"stream {b}: popped symbols differ"
+        assert got[b] == st.to_list(), f"stream {b}: state differs after pop"
+        ost.append(st)
+    sym = rs.randint(0, S, size=(B, L)).astype(np.int16)
+    sym[:, :4] = [0, S - 1, S // 2, 1]                       # edge bins
+    dsym = torch.from_numpy(sym).to(dev)
+    check(lib().bsw_logistic_push(ss.handle, 0, B, dmu.data_ptr(), L, dsc_arg.data_ptr(), sss, e_pad.data_ptr(), ers,
+                                  dsym.data_ptr(), L, S, 31, q, cuda_stream_ptr()))
+    ss.raise_on_error()
+    got = ss.export_lists()
+    for b in range(B):
+        want = O.AnsC(tables=tabs[b]).encode(ost[b], sym[b].astype(np.int64)).to_list()
+        assert got[b] == want, f"stream {b}: state differs after push"
+    # inverse: popping again returns the pushed symbols and the post-pop state
+    check(lib().bsw_logistic_pop(ss.handle, 0, B, dmu.data_ptr(), L, dsc_arg.data_ptr(), sss, e_pad.data_ptr(), ers,
+                                 out.data_ptr(), L, S, 31, q, cuda_stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), sym)
+    # materialised-table kernel == quantiser on our pmfs
+    P = torch.empty((L, S), dtype=torch.int32, device=dev)
+    C = torch.empty((L, S + 1), dtype=torch.int32, device=dev)
+    check(lib().bsw_logistic_tables(e_raw.data_ptr(), S - 1, dmu[0].double().contiguous().data_ptr(),
+                                    dsc[0].double().contiguous().data_ptr(), 1, L, S, 31, q, P.data_ptr(), C.data_ptr(),
+                                    cuda_stream_ptr()))
+    assert np.array_equal(P.cpu().numpy().view(np.uint32).astype(np.int64), tabs[0][0])
+    assert np.array_equal(C.cpu().numpy().view(np.uint32).astype(np.int64), tabs[0][1])
+
+
+def test_fused_underflow_flags_stream():
+    L, S, q = 512, 256, 8
+    rs = np.random.RandomState(0)
+    from bitswap_b200.rand import ImageBins
+    e_pad = torch.from_numpy(_pad_inf(ImageBins(torch.float64, "cpu", 1).endpoints().numpy())).to(dev)
+    mu = torch.from_numpy(rs.uniform(-1, 1, (2, L)).astype(np.float32)).to(dev)
+    sc = torch.full((1, L), 0.5, dtype=torch.float32, device=dev)
+    ss = StreamSet(2, 4096)
+    w, head = synthetic.initial_words(2000, seed=100)
+    ss.import_lists([[int(v) for v in w[:10]] + [head], [int(v) for v in w] + [head]])
+    out = torch.zeros((2, L), dtype=torch.int16, device=dev)
+    check(lib().bsw_logistic_pop(ss.handle, 0, 2, mu.data_ptr(), L, sc.data_ptr(), 0, e_pad.data_ptr(), 0,
+                                 out.data_ptr(), L, S, 31, q, cuda_stream_ptr()))
+    _, _, flags = ss.sizes()
+    assert flags.tolist() == [1, 0]
+    with pytest.raises(IndexError):
+        ss.raise_on_error()
