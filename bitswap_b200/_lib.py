@@ -74,7 +74,8 @@ def lib():
         L = ctypes.CDLL(SO_PATH)
         L.bsw_last_error.restype = ctypes.c_char_p
         L.bsw_streams_capacity.restype = ctypes.c_int64
-        L.bsw_codec_last_launches.restype = ctypes.c_int64
+        if hasattr(L, "bsw_codec_last_launches"):
+            L.bsw_codec_last_launches.restype = ctypes.c_int64
         _set_argtypes(L)
         _lib = L
     return _lib

@@ -215,8 +215,9 @@ def test_p2_fused_logistic_coder_vs_oracle_on_our_pmfs(B, L, S, q, kind):
     tabs = []
     for b in range(B):
         pm = torch.empty((L, S), dtype=torch.float64, device=dev)
-        check(lib().bsw_logistic_pmfs(e_raw.data_ptr(), S - 1, dmu[b].double().contiguous().data_ptr(),
-                                      dsc[b].double().contiguous().data_ptr(), 1, L, S, pm.data_ptr(), cuda_stream_ptr()))
+        mu64, sc64 = dmu[b].double().contiguous(), dsc[b].double().contiguous()     # keep alive across the call
+        check(lib().bsw_logistic_pmfs(e_raw.data_ptr(), S - 1, mu64.data_ptr(), sc64.data_ptr(), 1, L, S,
+                                      pm.data_ptr(), cuda_stream_ptr()))
         torch.cuda.synchronize()
         tabs.append(O.tables_c(pm.cpu().numpy(), 31, q))
     # pop first (bits-back), then push other symbols
@@ -249,9 +250,9 @@ def test_p2_fused_logistic_coder_vs_oracle_on_our_pmfs(B, L, S, q, kind):
     # materialised-table kernel == quantiser on our pmfs
     P = torch.empty((L, S), dtype=torch.int32, device=dev)
     C = torch.empty((L, S + 1), dtype=torch.int32, device=dev)
-    check(lib().bsw_logistic_tables(e_raw.data_ptr(), S - 1, dmu[0].double().contiguous().data_ptr(),
-                                    dsc[0].double().contiguous().data_ptr(), 1, L, S, 31, q, P.data_ptr(), C.data_ptr(),
-                                    cuda_stream_ptr()))
+    mu64, sc64 = dmu[0].double().contiguous(), dsc[0].double().contiguous()
+    check(lib().bsw_logistic_tables(e_raw.data_ptr(), S - 1, mu64.data_ptr(), sc64.data_ptr(), 1, L, S, 31, q,
+                                    P.data_ptr(), C.data_ptr(), cuda_stream_ptr()))
     assert np.array_equal(P.cpu().numpy().view(np.uint32).astype(np.int64), tabs[0][0])
     assert np.array_equal(C.cpu().numpy().view(np.uint32).astype(np.int64), tabs[0][1])
 
