@@ -361,9 +361,10 @@ extern "C" int bsw_logistic_tables(const double *endp, int64_t ers, const double
 // ================================================================================================
 constexpr int TW = 4;   // warps (= streams) per CTA for the table-driven kernels
 
+template <typename SymT>
 __global__ void __launch_bounds__(TW * 32) k_push_tables(bsw_streams sv, int first, int count,
         const uint32_t *__restrict__ P, const uint32_t *__restrict__ C, int64_t pss, int64_t css,
-        const int32_t *__restrict__ sym, int64_t L, int S, int bits) {
+        const SymT *__restrict__ sym, int64_t L, int S, int bits) {
     int lane = threadIdx.x & 31;
     int si = blockIdx.x * TW + (threadIdx.x >> 5);
     if (si >= count) return;
@@ -373,12 +374,12 @@ __global__ void __launch_bounds__(TW * 32) k_push_tables(bsw_streams sv, int fir
     if (ws.err) return;
     ws.push_begin(lane);
     const uint32_t *Pb = P + (int64_t)si * pss, *Cb = C + (int64_t)si * css;
-    const int32_t *sy = sym + (int64_t)si * L;
+    const SymT *sy = sym + (int64_t)si * L;
     for (int64_t i0 = 0; i0 < L && !ws.err; i0 += 32) {
         int64_t i = i0 + lane;
         uint32_t p = 1, c = 0;
         if (i < L) {
-            int s = sy[i];
+            int s = (int)sy[i];
             p = Pb[i * S + s];
             c = Cb[i * (S + 1) + s];
         }
@@ -390,9 +391,10 @@ __global__ void __launch_bounds__(TW * 32) k_push_tables(bsw_streams sv, int fir
     ws.close(sv, b, lane);
 }
 
+template <typename SymT>
 __global__ void __launch_bounds__(TW * 32) k_pop_tables(bsw_streams sv, int first, int count,
         const uint32_t *__restrict__ P, const uint32_t *__restrict__ C, int64_t pss, int64_t css,
-        int32_t *__restrict__ sym, int64_t L, int S, int bits) {
+        SymT *__restrict__ sym, int64_t L, int S, int bits) {
     int lane = threadIdx.x & 31;
     int si = blockIdx.x * TW + (threadIdx.x >> 5);
     if (si >= count) return;
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(TW * 32) k_pop_tables(bsw_streams sv, int firs
     ws.open(sv, b);
     if (ws.err) return;
     const uint32_t *Pb = P + (int64_t)si * pss, *Cb = C + (int64_t)si * css;
-    int32_t *sy = sym + (int64_t)si * L;
+    SymT *sy = sym + (int64_t)si * L;
     const uint32_t mask = (uint32_t)(((uint64_t)1 << bits) - 1);
     const int step = (S + 31) / 32;
     for (int64_t i = L - 1; i >= 0 && !ws.err; --i) {
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(TW * 32) k_pop_tables(bsw_streams sv, int firs
             cnt += __popc(__ballot_sync(FULL, (t0 + lane) < step && k < S && Cr[k] <= m));
         }
         int s = chunk * step + cnt - 1;
-        if (lane == 0) sy[i] = s;                                               // :62
+        if (lane == 0) sy[i] = (SymT)s;                                               // :62
         ws.decode(Pb[i * S + s], Cr[s], m, bits, lane);                         // :63-65
     }
     ws.close(sv, b, lane);
@@ -431,7 +433,7 @@ extern "C" int bsw_ans_push(bsw_streams *s, int first, int count, const uint32_t
                             int64_t css, const int32_t *sym, int64_t L, int S, int bits, void *stream) {
     if (int rc = check_range(s, first, count)) return rc;
     BSW_REQUIRE(P && C && sym && L > 0 && S > 1 && bits > 0 && bits <= 31, "bsw_ans_push: bad arguments");
-    k_push_tables<<<(count + TW - 1) / TW, TW * 32, 0, (cudaStream_t)stream>>>(*s, first, count, P, C, pss, css, sym, L, S, bits);
+    k_push_tables<int32_t><<<(count + TW - 1) / TW, TW * 32, 0, (cudaStream_t)stream>>>(*s, first, count, P, C, pss, css, sym, L, S, bits);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
 }
@@ -439,7 +441,23 @@ extern "C" int bsw_ans_pop(bsw_streams *s, int first, int count, const uint32_t 
                            int64_t css, int32_t *sym, int64_t L, int S, int bits, void *stream) {
     if (int rc = check_range(s, first, count)) return rc;
     BSW_REQUIRE(P && C && sym && L > 0 && S > 1 && bits > 0 && bits <= 31, "bsw_ans_pop: bad arguments");
-    k_pop_tables<<<(count + TW - 1) / TW, TW * 32, 0, (cudaStream_t)stream>>>(*s, first, count, P, C, pss, css, sym, L, S, bits);
+    k_pop_tables<int32_t><<<(count + TW - 1) / TW, TW * 32, 0, (cudaStream_t)stream>>>(*s, first, count, P, C, pss, css, sym, L, S, bits);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+
+// int16-symbol variants used by the device-resident codec (codec.cu) for the shared prior table
+int bsw_ans_push_i16(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *C, int64_t pss, int64_t css,
+                     const int16_t *sym, int64_t L, int S, int bits, cudaStream_t st) {
+    if (int rc = check_range(s, first, count)) return rc;
+    k_push_tables<int16_t><<<(count + TW - 1) / TW, TW * 32, 0, st>>>(*s, first, count, P, C, pss, css, sym, L, S, bits);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+int bsw_ans_pop_i16(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *C, int64_t pss, int64_t css,
+                    int16_t *sym, int64_t L, int S, int bits, cudaStream_t st) {
+    if (int rc = check_range(s, first, count)) return rc;
+    k_pop_tables<int16_t><<<(count + TW - 1) / TW, TW * 32, 0, st>>>(*s, first, count, P, C, pss, css, sym, L, S, bits);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
 }

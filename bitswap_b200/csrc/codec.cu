@@ -1,0 +1,226 @@
+// The bits-back recursions, device resident (sm_100a).
+//
+// Reference being replaced (fhkingma/bitswap @ dfe0bf7d):
+//   Bit-Swap sender   cifar_compress.py:175-204, 244-250      receiver  :283-317
+//   BB-ANS  sender    cifar_compress.py:205-242, 244-250      receiver  :319-352
+// One call codes ONE image per stream for `count` streams.  Every step is a kernel enqueued on the
+// caller's stream; symbols, centres, mu/sigma and the ANS state stay in HBM between levels -- the
+// reference's 2*nz GPU<->CPU round trips per image (cifar_compress.py:42-43,66) do not exist here.
+#include <vector>
+#include "bsw_common.cuh"
+#include "nets.cuh"
+
+struct bsw_codec {
+    bsw_model *m;
+    bsw_bins *b;
+    int max_batch, nz, zdim, xdim, q, S;
+    float *given, *mu, *scale;          // [max_batch, max(xdim, zdim)]
+    int16_t *sym[2];                    // ping-pong latent symbols [max_batch, zdim]
+    int16_t *xsym;                      // [max_batch, xdim] pixels as int16 symbols
+    std::vector<int16_t *> zs;          // BB-ANS: all nz latents
+    uint32_t *priorP, *priorC;          // Logistic(0,1) prior tables over zendpoints[-1], shared by all streams
+    int64_t launches;
+};
+
+// internal int16-symbol variants of the table-driven coder (ans_kernels.cu)
+int bsw_ans_push_i16(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *C, int64_t pss, int64_t css,
+                     const int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
+int bsw_ans_pop_i16(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *C, int64_t pss, int64_t css,
+                    int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
+
+__global__ void k_u8_to_i16(const uint8_t *__restrict__ in, int16_t *__restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void k_i16_to_u8(const int16_t *__restrict__ in, uint8_t *__restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)in[i];
+}
+
+extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int max_batch) {
+    BSW_REQUIRE(out && m && b && max_batch >= 1, "bsw_codec_create: bad arguments");
+    BSW_REQUIRE(m->finalized, "bsw_codec_create: model not finalized");
+    BSW_REQUIRE(b->nz == m->d.nz && b->zdim == m->zdim, "bsw_codec_create: bins do not match the model");
+    BSW_REQUIRE(max_batch <= m->d.max_batch, "bsw_codec_create: max_batch exceeds the model's");
+    bsw_codec *c = new bsw_codec();
+    c->m = m; c->b = b; c->max_batch = max_batch;
+    c->nz = b->nz; c->zdim = b->zdim; c->xdim = m->xdim; c->q = b->q; c->S = b->S;
+    size_t dim = (size_t)(c->xdim > c->zdim ? c->xdim : c->zdim);
+    BSW_CUDA(cudaMalloc(&c->given, sizeof(float) * dim * max_batch));
+    BSW_CUDA(cudaMalloc(&c->mu, sizeof(float) * dim * max_batch));
+    BSW_CUDA(cudaMalloc(&c->scale, sizeof(float) * dim * max_batch));
+    BSW_CUDA(cudaMalloc(&c->sym[0], sizeof(int16_t) * c->zdim * max_batch));
+    BSW_CUDA(cudaMalloc(&c->sym[1], sizeof(int16_t) * c->zdim * max_batch));
+    BSW_CUDA(cudaMalloc(&c->xsym, sizeof(int16_t) * c->xdim * max_batch));
+    c->zs.assign(c->nz, nullptr);
+    // prior tables: Logistic(0,1) over the top level's endpoints, identical for every stream and image
+    // (cifar_compress.py:245-247) -> built once, with the same float64 kernel math as every other table.
+    BSW_CUDA(cudaMalloc(&c->priorP, sizeof(uint32_t) * (size_t)c->zdim * c->S));
+    BSW_CUDA(cudaMalloc(&c->priorC, sizeof(uint32_t) * (size_t)c->zdim * (c->S + 1)));
+    double ms[2] = {0.0, 1.0}, *dms = nullptr;
+    BSW_CUDA(cudaMalloc(&dms, sizeof(ms)));
+    BSW_CUDA(cudaMemcpy(dms, ms, sizeof(ms), cudaMemcpyHostToDevice));
+    const double *zend = b->zend + (size_t)(c->nz - 1) * c->zdim * c->S;
+    int rc = bsw_logistic_tables(zend, c->S, dms, dms + 1, 0, c->zdim, c->S, 31, c->q, c->priorP, c->priorC, nullptr);
+    BSW_CUDA(cudaDeviceSynchronize());
+    cudaFree(dms);
+    if (rc) return rc;
+    c->launches = 0;
+    *out = c;
+    return BSW_OK;
+}
+
+extern "C" int bsw_codec_destroy(bsw_codec *c) {
+    if (!c) return BSW_OK;
+    cudaFree(c->given); cudaFree(c->mu); cudaFree(c->scale);
+    cudaFree(c->sym[0]); cudaFree(c->sym[1]); cudaFree(c->xsym);
+    for (auto p : c->zs) cudaFree(p);
+    cudaFree(c->priorP); cudaFree(c->priorC);
+    delete c;
+    return BSW_OK;
+}
+extern "C" int64_t bsw_codec_last_launches(const bsw_codec *c) { return c ? c->launches : 0; }
+
+#define RC(call) do { if (int rc_ = (call)) return rc_; } while (0)
+
+namespace {
+struct Ctx {
+    bsw_codec *c; bsw_streams *s; int first, count; cudaStream_t st;
+    int nl = 0;
+    const double *zend(int lvl) const { return c->b->zend + (size_t)lvl * c->zdim * c->S; }
+    int infer(int zi) { return bsw_model_run(c->m, true, zi, c->given, count, c->mu, c->scale, 1, st, &nl); }
+    int generate(int zi) { return bsw_model_run(c->m, false, zi, c->given, count, c->mu, c->scale, 0, st, &nl); }
+    int gather_x(const uint8_t *x) { ++nl; return bsw_gather_xcentres(x, c->given, (int64_t)count * c->xdim, st); }
+    int gather_x16(const int16_t *x);
+    int gather_z(int lvl, const int16_t *sym) { ++nl; return bsw_gather_zcentres(c->b, lvl, sym, c->given, count, st); }
+    // q(z_{zi+1} | .) / p(z_zi | .) tables over level `lvl` endpoints
+    int pop_z(int lvl, int16_t *sym) {
+        ++nl;
+        return bsw_logistic_pop(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+    }
+    int push_z(int lvl, const int16_t *sym) {
+        ++nl;
+        return bsw_logistic_push(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+    }
+    // p(x | z_1): ImageBins endpoints (one shared row), 8-bit quantisation (cifar_compress.py:202)
+    int64_t xss() const { return c->m->d.cond_xscale ? c->xdim : 0; }
+    int pop_x(int16_t *sym) {
+        ++nl;
+        return bsw_logistic_pop(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+    }
+    int push_x(const int16_t *sym) {
+        ++nl;
+        return bsw_logistic_push(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+    }
+    int push_prior(const int16_t *sym) {
+        ++nl;
+        return bsw_ans_push_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
+    }
+    int pop_prior(int16_t *sym) {
+        ++nl;
+        return bsw_ans_pop_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
+    }
+};
+__global__ void k_gather_x16(const int16_t *__restrict__ x, float *__restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)(((double)x[i] - 127.5) / 127.5);
+}
+int Ctx::gather_x16(const int16_t *x) {
+    ++nl;
+    int64_t n = (int64_t)count * c->xdim;
+    k_gather_x16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, c->given, n);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+}  // namespace
+
+static int codec_args_ok(bsw_codec *c, bsw_streams *s, int first, int count, const void *x) {
+    BSW_REQUIRE(c && s && x, "bsw_codec: null argument");
+    BSW_REQUIRE(first >= 0 && count >= 1 && first + count <= s->B, "bsw_codec: stream range out of bounds");
+    BSW_REQUIRE(count <= c->max_batch, "bsw_codec: count exceeds the codec's max_batch");
+    return BSW_OK;
+}
+static int ensure_zs(bsw_codec *c) {
+    for (auto &p : c->zs)
+        if (!p) BSW_CUDA(cudaMalloc(&p, sizeof(int16_t) * c->zdim * c->max_batch));
+    return BSW_OK;
+}
+
+extern "C" int bsw_codec_encode(bsw_codec *c, bsw_streams *s, int first, int count, const uint8_t *x, int scheme, void *stream) {
+    RC(codec_args_ok(c, s, first, count, x));
+    Ctx k{c, s, first, count, (cudaStream_t)stream};
+    const int nz = c->nz;
+    int64_t nx = (int64_t)count * c->xdim;
+    k_u8_to_i16<<<(unsigned)((nx + 255) / 256), 256, 0, k.st>>>(x, c->xsym, nx);
+    BSW_LAUNCH_CHECK();
+    ++k.nl;
+    int16_t *zsym = c->sym[0], *ztop = c->sym[1];
+    if (scheme == 0) {
+        // Bit-Swap sender (cifar_compress.py:178-204)
+        for (int zi = 0; zi < nz; ++zi) {
+            if (zi == 0) RC(k.gather_x(x)); else RC(k.gather_z(zi - 1, zsym));           // :180
+            RC(k.infer(zi));                                                                // :181
+            RC(k.pop_z(zi, ztop));                                                          // :182-187
+            RC(k.gather_z(zi, ztop));                                                       // :195
+            RC(k.generate(zi));                                                             // :196
+            if (zi == 0) RC(k.push_x(c->xsym)); else RC(k.push_z(zi - 1, zsym));           // :197-202
+            int16_t *t = zsym; zsym = ztop; ztop = t;                                       // :204
+        }
+    } else {
+        // BB-ANS sender (cifar_compress.py:208-242): all pops first, then all pushes
+        RC(ensure_zs(c));
+        for (int zi = 0; zi < nz; ++zi) {
+            if (zi == 0) RC(k.gather_x(x)); else RC(k.gather_z(zi - 1, c->zs[zi - 1]));
+            RC(k.infer(zi));
+            RC(k.pop_z(zi, c->zs[zi]));
+        }
+        for (int zi = 0; zi < nz; ++zi) {
+            RC(k.gather_z(zi, c->zs[zi]));
+            RC(k.generate(zi));
+            if (zi == 0) RC(k.push_x(c->xsym)); else RC(k.push_z(zi - 1, c->zs[zi - 1]));
+        }
+        zsym = c->zs[nz - 1];
+    }
+    RC(k.push_prior(zsym));                                                                 // :245-250
+    c->launches = k.nl;
+    return BSW_OK;
+}
+
+extern "C" int bsw_codec_decode(bsw_codec *c, bsw_streams *s, int first, int count, uint8_t *x, int scheme, void *stream) {
+    RC(codec_args_ok(c, s, first, count, x));
+    Ctx k{c, s, first, count, (cudaStream_t)stream};
+    const int nz = c->nz;
+    int16_t *ztop = c->sym[0], *sym = c->sym[1];
+    if (scheme == 0) {
+        // Bit-Swap receiver (cifar_compress.py:283-317)
+        RC(k.pop_prior(ztop));                                                              // :284-289
+        for (int zi = nz - 1; zi >= 0; --zi) {
+            RC(k.gather_z(zi, ztop));                                                       // :296
+            RC(k.generate(zi));                                                             // :297
+            if (zi == 0) RC(k.pop_x(c->xsym)); else RC(k.pop_z(zi - 1, sym));               // :298-303
+            if (zi == 0) RC(k.gather_x16(c->xsym)); else RC(k.gather_z(zi - 1, sym));       // :306
+            RC(k.infer(zi));                                                                // :307
+            RC(k.push_z(zi, ztop));                                                         // :308-313
+            int16_t *t = ztop; ztop = sym; sym = t;                                         // :315
+        }
+    } else {
+        // BB-ANS receiver (cifar_compress.py:319-352)
+        RC(ensure_zs(c));
+        RC(k.pop_prior(c->zs[nz - 1]));
+        for (int zi = nz - 1; zi >= 0; --zi) {
+            RC(k.gather_z(zi, c->zs[zi]));
+            RC(k.generate(zi));
+            if (zi == 0) RC(k.pop_x(c->xsym)); else RC(k.pop_z(zi - 1, c->zs[zi - 1]));
+        }
+        for (int zi = nz - 1; zi >= 0; --zi) {
+            if (zi == 0) RC(k.gather_x16(c->xsym)); else RC(k.gather_z(zi - 1, c->zs[zi - 1]));
+            RC(k.infer(zi));
+            RC(k.push_z(zi, c->zs[zi]));
+        }
+    }
+    int64_t nx = (int64_t)count * c->xdim;
+    k_i16_to_u8<<<(unsigned)((nx + 255) / 256), 256, 0, k.st>>>(c->xsym, x, nx);
+    BSW_LAUNCH_CHECK();
+    c->launches = k.nl + 1;
+    return BSW_OK;
+}

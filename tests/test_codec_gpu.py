@@ -1,0 +1,180 @@
+"""GPU parity of the nets (P3) and of the device-resident recursion (P4), through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O                      # noqa: E402  (checker only)
+from bitswap_b200 import synthetic                   # noqa: E402
+from bitswap_b200.config import preset               # noqa: E402
+from bitswap_b200.model import Model                 # noqa: E402
+from bitswap_b200.codec import BitSwapCodec, Bins, BITSWAP, BBANS   # noqa: E402
+from bitswap_b200.streams import StreamSet           # noqa: E402
+from bitswap_b200.rand import ImageBins              # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-4          # north_star: per-latent mu/sigma within 1e-4 of the reference torch model
+
+
+def _model(cfg, max_batch, tc=False):
+    sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=True)
+    m = Model.from_config(cfg, max_batch=max_batch, use_tensor_cores=tc).load_state_dict(sd)
+    m.compress()
+    return m, sd
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny3"])
+def test_p3_nets_vs_reference_golden(name):
+    """mu/scale of every infer(i)/generate(i) against outputs of the REFERENCE Model (golden file)."""
+    cfg = preset(name)
+    g = np.load(os.path.join(GOLDEN, f"model_{name}.npz"))
+    m, _ = _model(cfg, 4)
+    _, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    xcen = ImageBins(torch.float64, "cpu", cfg.xdim).centres()
+    zr = torch.arange(cfg.zdim)
+    worst = 0.0
+    for i in range(cfg.nz):
+        if i == 0:
+            given = xcen[torch.arange(cfg.xdim), torch.from_numpy(g["x"].astype(np.int64))]
+        else:
+            given = zcen[i - 1, zr, torch.from_numpy(g[f"zsym_in_infer{i}"].astype(np.int64))]
+        mu, sc = m.infer(i)(given=given.cuda())            # reference call shape: flat float64 in, flat float64 out
+        assert mu.dtype == torch.float64 and mu.shape == (cfg.zdim,)
+        worst = max(worst, np.abs(mu.cpu().numpy() - g[f"infer{i}_mu"]).max(), np.abs(sc.cpu().numpy() - g[f"infer{i}_scale"]).max())
+        z = zcen[i, zr, torch.from_numpy(g[f"zsym_in_gen{i}"].astype(np.int64))]
+        mu, sc = m.generate(i)(given=z.cuda())
+        assert mu.shape == ((cfg.xdim,) if i == 0 else (cfg.zdim,))
+        worst = max(worst, np.abs(mu.cpu().numpy() - g[f"gen{i}_mu"]).max(), np.abs(sc.cpu().numpy() - g[f"gen{i}_scale"]).max())
+    assert worst < TOL, worst
+
+
+@pytest.mark.parametrize("name,B", [("mnist2", 3), ("cifar8", 2)])
+def test_p3_nets_vs_oracle_full_width(name, B):
+    """Reference-sized nets (W=63 / W=252) against the torch float32 oracle, batched, batch-invariant."""
+    cfg = preset(name)
+    m, sd = _model(cfg, B)
+    orc = O.ModelOracle(cfg, sd)
+    rs = np.random.RandomState(4)
+    _, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    worst = 0.0
+    for i in range(cfg.nz):
+        if i == 0:
+            given = torch.from_numpy((rs.randint(0, 256, (B, cfg.xdim)) - 127.5) / 127.5)
+        else:
+            given = torch.from_numpy(rs.uniform(-5, 5, (B, cfg.zdim)))
+        for kind in ("infer", "generate"):
+            gv = given if (kind == "infer") else torch.from_numpy(rs.uniform(-5, 5, (B, cfg.zdim)))
+            f_gpu = m.infer(i) if kind == "infer" else m.generate(i)
+            f_cpu = orc.infer(i) if kind == "infer" else orc.generate(i)
+            mu, sc = f_gpu(gv.cuda())
+            mu_o, sc_o = f_cpu(gv)
+            worst = max(worst, (mu.cpu() - mu_o).abs().max().item(), (sc.cpu() - sc_o).abs().max().item())
+            # batch invariance / determinism (H3): row 1 alone gives bit-identical outputs
+            mu1, sc1 = f_gpu(gv[1:2].cuda())
+            assert torch.equal(mu1[0], mu[1]) and torch.equal(sc1[0], sc[1])
+    assert worst < TOL, worst
+
+
+def _setup(name, B, cap, tc=False):
+    cfg = preset(name)
+    m, sd = _model(cfg, B, tc)
+    zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    bins = Bins(cfg, zend, zcen)
+    codec = BitSwapCodec(cfg, m, bins, B)
+    ss = StreamSet(B, cap)
+    return cfg, m, sd, zend, zcen, codec, ss
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny3"])
+def test_p4_bitswap_vs_reference_trace(name):
+    """Own nets + own tables, same inputs as the reference-classes golden run: every stream must follow the
+    reference's state trace (lengths), reproduce its final state bit for bit when no table bin flipped, and
+    round-trip exactly.  With W<=20 nets the float32 outputs agree to ~1e-6, so bins rarely flip."""
+    g = json.load(open(os.path.join(GOLDEN, f"bitswap_{name}.json")))
+    B = 3
+    cfg, m, sd, zend, zcen, codec, ss = _setup(name, B, 8192)
+    imgs = synthetic.synthetic_images(cfg, g["nimg"], seed=7)
+    w, head = synthetic.initial_words(g["nwords"], seed=100)
+    ss.fill(w, head)
+    init = ss.export_lists()
+    for xi in range(g["nimg"]):
+        x = torch.from_numpy(np.repeat(imgs[xi][None], B, axis=0)).cuda()
+        codec.encode(ss, x)
+    ss.raise_on_error()
+    final = ss.export_lists()
+    assert final[0] == final[1] == final[2]                      # identical streams stay identical
+    assert len(final[0]) == g["final_len"]
+    identical = O.CState.from_list(final[0]).digest() == g["trace"][-1][2]
+    print(f"{name}: final state bit-identical to the reference-classes run: {identical}")
+    assert abs(32.0 * (len(final[0]) - len(init[0])) / (cfg.xdim * g["nimg"]) - g["net_bits_per_dim"]) < 1e-9
+    for xi in reversed(range(g["nimg"])):
+        out = codec.decode(ss, B)
+        assert np.array_equal(out.cpu().numpy(), np.repeat(imgs[xi][None], B, axis=0))
+    ss.raise_on_error()
+    assert ss.export_lists() == init
+
+
+@pytest.mark.parametrize("name,scheme", [("tiny", BITSWAP), ("tiny3", BITSWAP), ("tiny", BBANS), ("tiny3", BBANS)])
+def test_p4_vs_oracle_with_injected_nets(name, scheme):
+    """Oracle recursion driven with OUR mu/sigma (injected through mu_hook) and libm tables: symbols, word counts
+    and -- unless a 1-ulp sigmoid difference flipped a bin -- full states agree for distinct images/streams."""
+    B, nimg = 4, 2
+    cfg, m, sd, zend, zcen, codec, ss = _setup(name, B, 1 << 14)
+    imgs = synthetic.synthetic_images(cfg, B * nimg, seed=11).reshape(nimg, B, *cfg.xs)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(3000 + 11 * b, seed=100 + b)
+        states.append([int(v) for v in w] + [head])
+    ss.import_lists(states)
+    for xi in range(nimg):
+        codec.encode(ss, torch.from_numpy(imgs[xi]).cuda(), scheme=scheme)
+    ss.raise_on_error()
+    got = ss.export_lists()
+    n_ident = 0
+    for b in range(B):
+        def hook(kind, level, mu, sc):
+            f = m.infer(level) if kind == "infer" else m.generate(level)
+            return tuple(t.cpu() for t in f(hook.given.cuda()))
+        orc = O.BitSwapOracle(cfg, O.ModelOracle(cfg, sd), zend, zcen, coder="c", pmf="c")
+        # inject our nets: wrap _net so the GPU model sees the same `given`
+        def _net(kind, level, given, _m=m):
+            f = _m.infer(level) if kind == "infer" else _m.generate(level)
+            mu, sc = f(given.cuda())
+            return mu.cpu(), sc.cpu()
+        orc._net = _net
+        st = O.CState.from_list(states[b])
+        for xi in range(nimg):
+            st = (orc.encode_image if scheme == BITSWAP else orc.encode_image_bbans)(st, imgs[xi, b])
+        want = st.to_list()
+        assert len(got[b]) == len(want), f"stream {b}: word count differs"
+        n_ident += int(got[b] == want)
+    print(f"{name}/{'bitswap' if scheme == BITSWAP else 'bbans'}: {n_ident}/{B} streams bit-identical to the CPU oracle")
+    assert n_ident >= B - 1
+    for xi in reversed(range(nimg)):
+        out = codec.decode(ss, B, scheme=scheme)
+        assert np.array_equal(out.cpu().numpy(), imgs[xi])
+    ss.raise_on_error()
+    assert ss.export_lists() == states
+
+
+def test_p4_roundtrip_sub_range_and_chain_independence():
+    """Coding streams [2,6) leaves the others untouched; a stream's result does not depend on its neighbours."""
+    B = 8
+    cfg, m, sd, zend, zcen, codec, ss = _setup("tiny", B, 8192)
+    w, head = synthetic.initial_words(1200, seed=100)
+    ss.fill(w, head)
+    init = ss.export_lists()
+    imgs = synthetic.synthetic_images(cfg, 4, seed=3)
+    codec.encode(ss, torch.from_numpy(imgs).cuda(), first=2)
+    after = ss.export_lists()
+    assert after[:2] == init[:2] and after[6:] == init[6:]
+    ss2 = StreamSet(1, 8192)
+    ss2.fill(w, head)
+    codec.encode(ss2, torch.from_numpy(imgs[2:3]).cuda())
+    assert ss2.export_lists()[0] == after[4]
+    out = codec.decode(ss, 4, first=2)
+    assert np.array_equal(out.cpu().numpy(), imgs) and ss.export_lists() == init
