@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- Bit-Swap encode+decode throughput on B200 (BASELINE.json metric).
+
+A "step" = one pass of the hot path over one batch: Bit-Swap ENCODE of B images (one per ANS stream)
+followed by Bit-Swap DECODE of the same B images, CIFAR-shaped 32x32x3 uint8, 8-latent VAE
+(configs[1] of BASELINE.json: batch 1024 per GPU).  Decode restores every stream to its initial
+state, so steps repeat without re-initialisation.
+
+  value        Mpixel/s (pixel = H*W, 1024 per image) over encode+decode, inputs resident in HBM,
+               CUDA-event timed, max over ranks; whole-job aggregate over N GPUs (weak scaling:
+               per-GPU batch fixed, streams sharded by rank, no collective on the data path).
+  e2e          same metric through the public Python/C-ABI API with HOST buffers: pinned uint8 pixels
+               -> device -> encode -> packed bitstream to host -> back to device -> decode -> pixels
+               to host, all copies inside the timed region.
+  roofline     dominant kernel category (per-kernel CUDA events inside the timed region).
+  cpu_baseline the oracle port (reference algorithm: torch-CPU nets + float64 tables + Python-loop ANS)
+               on a bounded sample, on this box's host cores.
+
+`--impl reference` times that CPU path as its own arm (the reference is pure Python and cannot be
+pip-installed/travel).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bitswap_b200 import synthetic                        # noqa: E402
+from bitswap_b200.config import preset                    # noqa: E402
+
+METRIC = "Mpixels/sec encode+decode (Bit-Swap, 32x32x3, 8-latent VAE)"
+UNIT = "Mpixel/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------
+# work accounting (DESIGN.md "Roofline accounting")
+# ----------------------------------------------------------------------------------------------------
+def conv_flops(cfg):
+    """Algorithmic 2*MAC of the UNPADDED reference convs per image and direction."""
+    W, zc, C = cfg.reswidth, cfg.zchannels, cfg.xs[0]
+    px = 256
+    rd = cfg.level_resdepth
+    d3 = 2 * px * W * 9 * W          # one 3x3 W->W conv
+    d5 = 2 * px * W * 25 * W
+    n3 = 2 * sum(rd) * 2             # infer+gen, conv1+conv2 per layer
+    n5 = 2 * cfg.nprocessing * 2
+    small = 2 * px * (4 * C * 25 * W) + (2 * cfg.nz - 1) * 2 * px * (zc * 9 * W) \
+        + (2 * cfg.nz - 1) * 2 * px * (W * 9 * 2 * zc) + 2 * px * (W * 9 * 4 * C * (2 if cfg.cond_xscale else 1))
+    return dict(dense3=d3, n3=n3, dense5=d5, n5=n5, small=small, total=n3 * d3 + n5 * d5 + small)
+
+
+def ans_bytes(cfg):
+    """Compulsory HBM bytes per image and direction: mu,sigma float32 + int16 symbol per symbol-op
+    (x-level sigma is a shared parameter unless cond_xscale; the prior has neither)."""
+    z, x, nz = cfg.zdim, cfg.xdim, cfg.nz
+    return dict(pop_z=nz * z * 10, push_z=(nz - 1) * z * 10, push_x=x * (10 if cfg.cond_xscale else 6), prior=z * 2)
+
+
+def sigmoids(cfg):
+    z, x, nz, S = cfg.zdim, cfg.xdim, cfg.nz, cfg.zsupport
+    return dict(pop_z=nz * z * (S - 1), push_z=(nz - 1) * z * (S - 1), push_x=x * 255)
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port) -- bounded sample
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_sample(cfg, nimg, coder="port", threads=None):
+    """Times the reference algorithm on the host: chain of `nimg` images, encode then decode.
+    Returns (seconds_encode, seconds_decode, bits_per_dim)."""
+    from oracle import oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=False)
+    zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    bs = O.BitSwapOracle(cfg, O.ModelOracle(cfg, sd), zend, zcen, coder=coder, pmf="torch")
+    imgs = synthetic.synthetic_images(cfg, nimg, seed=7)
+    w, head = synthetic.initial_words(4096, seed=100)
+    st = ([int(v) for v in w] + [head]) if coder == "port" else O.CState(w, head)
+    n0 = len(st) if coder == "port" else st.n + 1
+    t0 = time.perf_counter()
+    for i in range(nimg):
+        st = bs.encode_image(st, imgs[i])
+    t1 = time.perf_counter()
+    n1 = len(st) if coder == "port" else st.n + 1
+    for i in reversed(range(nimg)):
+        st, x = bs.decode_image(st)
+        assert np.array_equal(x, imgs[i].reshape(-1))
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, 32.0 * (n1 - n0) / (cfg.xdim * nimg)
+
+
+def run_reference_arm(args, cfg, rank, world):
+    if rank != 0:
+        return
+    nimg = args.ref_images
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_reference_sample(cfg, 1)
+    t_enc = t_dec = 0.0
+    bpd = 0.0
+    for _ in range(args.steps):
+        e, d, bpd = cpu_reference_sample(cfg, nimg)
+        t_enc += e; t_dec += d
+    px = args.steps * nimg * 1024
+    val = px / (t_enc + t_dec) / 1e6
+    sample = f"{nimg}-image chain per step, encode then decode, batch=1 (reference is strictly batch 1)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (t_enc + t_dec) / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 tables / f32 nets / int64 coder", "data": "synthetic",
+            "config": {"workload": f"{args.config}: CIFAR-shaped 32x32x3 uint8, nz={cfg.nz}, W={cfg.reswidth}; {sample}",
+                       "what_runs": "oracle port of the reference path (torch-CPU nets, torch float64 logistic tables, "
+                                    "Python-loop ANS with Python ints) -- the reference itself is pure Python and cannot travel"},
+            "encode_Mpixel_s": args.steps * nimg * 1024 / t_enc / 1e6, "decode_Mpixel_s": args.steps * nimg * 1024 / t_dec / 1e6,
+            "bits_per_dim": bpd,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cifar8")
+    ap.add_argument("--batch", type=int, default=1024, help="streams (= images per step) PER GPU")
+    ap.add_argument("--tensor-cores", type=int, default=-1, help="-1 auto, 0 SIMT fp32 convs, 1 tcgen05")
+    ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-images", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = preset(args.config)
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank, world)
+        return
+
+    import torch.distributed as dist
+    from bitswap_b200.model import Model
+    from bitswap_b200.codec import BitSwapCodec, Bins
+    from bitswap_b200.streams import StreamSet
+    from bitswap_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    peaks = measured_peaks()
+
+    B = args.batch
+    use_tc = args.tensor_cores
+    if use_tc < 0:
+        use_tc = 1 if (_lib.has_tensor_core_path() and (cfg.reswidth + 63) // 64 * 64 == 256) else 0
+    sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=False)          # default-init distribution
+    model = Model.from_config(cfg, max_batch=B, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
+    model.compress()
+    zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    bins = Bins(cfg, zend, zcen)
+    codec = BitSwapCodec(cfg, model, bins, B)
+    ss = StreamSet(B, 4096 + 2048)
+    w, head = synthetic.initial_words(4096, seed=100)
+    ss.fill(w, head)
+    x_host = torch.from_numpy(synthetic.synthetic_images(cfg, B, seed=7 + rank)).pin_memory()
+    x_dev = x_host.to(dev)
+    out_dev = torch.empty_like(x_dev)
+    out_host = torch.empty_like(x_host).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- correctness outside the timed region: round trip + bits/dim -------------------------------
+    n0, _, _ = ss.sizes()
+    codec.encode(ss, x_dev)
+    n1, _, f1 = ss.sizes()
+    launches_enc = codec.last_launches
+    bits_per_dim = float(32.0 * (n1 - n0).mean() / cfg.xdim)
+    codec.decode(ss, B, out=out_dev)
+    n2, h2, f2 = ss.sizes()
+    launches_dec = codec.last_launches
+    roundtrip_ok = bool(torch.equal(out_dev, x_dev) and np.array_equal(n2, n0) and not f1.any() and not f2.any()
+                        and (h2 == np.uint64(head)).all())
+    assert roundtrip_ok, "round trip failed"
+
+    # ---- device-resident timing ----------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        codec.encode(ss, x_dev)
+        codec.decode(ss, B, out=out_dev)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    codec.profile(True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        codec.encode(ss, x_dev)
+        ev[2 * i + 1].record()
+        codec.decode(ss, B, out=out_dev)
+        ev[2 * i + 2].record()
+    torch.cuda.synchronize()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    enc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
+    dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps))
+    prof = codec.profile(False)
+    clocks = sampler.stop() if sampler else None
+    barrier()
+    t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms = t.tolist()
+    px_job = world * B * 1024 * args.steps
+    value = px_job / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end with host buffers ----------------------------------------------------------------
+    def e2e_step():
+        x_d = x_host.to(dev, non_blocking=True)                                   # H2D pixels
+        codec.encode(ss, x_d)
+        words, offs, heads, flags = ss.export()                                   # D2H bitstream (+ sizes, heads)
+        ss.import_packed(words, offs, heads)                                      # H2D bitstream (the receiver's side)
+        o = codec.decode(ss, B, out=out_dev)
+        out_host.copy_(o, non_blocking=True)                                      # D2H pixels
+        torch.cuda.synchronize()
+        return int(words.nbytes + offs.nbytes + heads.nbytes)
+
+    bs_bytes = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bs_bytes = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = t.item()
+    e2e_val = px_job / e2e_s / 1e6
+    assert torch.equal(out_host, x_host)
+
+    # ---- gather the final bitstreams over NCCL (only collective; outside the coder) -------------------
+    gather_ms = None
+    total_bits = float(32.0 * (n1 - n0).sum())
+    if world > 1:
+        codec.encode(ss, x_dev)
+        torch.cuda.synchronize()
+        words, offs, heads, flags = ss.export()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        lens = torch.from_numpy(np.diff(offs).astype(np.int32)).to(dev)
+        pad = torch.zeros(int(ss.capacity) * B, dtype=torch.int32, device=dev)
+        pad[:words.size] = torch.from_numpy(words.view(np.int32)).to(dev)
+        g0.record()
+        all_lens = [torch.empty_like(lens) for _ in range(world)]
+        dist.all_gather(all_lens, lens)
+        mx = torch.tensor([words.size], device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        buf = pad[:int(mx.item())].contiguous()
+        all_words = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(all_words, buf)
+        tb = torch.tensor([total_bits], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        total_bits = tb.item()
+        codec.decode(ss, B, out=out_dev)
+        torch.cuda.synchronize()
+
+    # ---- roofline for the dominant kernel category ---------------------------------------------------------
+    fl, ab, sg = conv_flops(cfg), ans_bytes(cfg), sigmoids(cfg)
+    per_launch = {     # algorithmic work of ONE launch (B images, one direction)
+        "conv_dense5x5": ("tensor", fl["dense5"] * B), "conv_dense3x3": ("tensor", fl["dense3"] * B),
+        "pop_z": ("hbm", cfg.zdim * 10 * B), "push_z": ("hbm", cfg.zdim * 10 * B),
+        "pop_x": ("hbm", ab["push_x"] * B), "push_x": ("hbm", ab["push_x"] * B),
+    }
+    kernels = {}
+    for k, (ms, n) in prof.items():
+        if n == 0:
+            continue
+        rec = {"ms_total": ms, "launches": n, "avg_ms": ms / n, "share": ms / max(sum(v[0] for v in prof.values()), 1e-9)}
+        if k in per_launch:
+            bound, work = per_launch[k]
+            if bound == "tensor":
+                rec.update(bound="tensor", achieved=work / (ms / n * 1e-3) / 1e12, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s")
+            else:
+                rec.update(bound="hbm", achieved=work / (ms / n * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+                nsig = {"pop_z": cfg.zdim * (cfg.zsupport - 1), "push_z": cfg.zdim * (cfg.zsupport - 1), "pop_x": cfg.xdim * 255,
+                        "push_x": cfg.xdim * 255}[k] * B
+                rec["f64_sigmoids_per_s"] = nsig / (ms / n * 1e-3)
+            rec["frac"] = rec["achieved"] / rec["peak"]
+        kernels[k] = rec
+    dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["ms_total"])
+    roofline = {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"], "peak": kernels[dom]["peak"],
+                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": None,
+                "peak_source": peaks["source"] + (" bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else " hbm_gbs"),
+                "share_of_step": kernels[dom]["share"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 tables / int64 coder / " + ("bf16x3 split tcgen05" if use_tc else "f32 SIMT") + " convs",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: CIFAR-shaped 32x32x3 uint8, nz={cfg.nz}, W={cfg.reswidth}, q={cfg.quantbits}; "
+                                   f"{B} independent ANS streams per GPU x 1 image per step; step = Bit-Swap encode + decode",
+                       "streams_per_gpu": B, "global_batch": B * world, "weights": "seeded random init (reference default-init distribution)",
+                       "bins": "synthetic uniform grids + float32 equal-mass top level", "images": "iid uniform uint8",
+                       "l2": "per-step working set (3 x 268 MB activations + streams) >> 126 MB L2: no explicit flush needed",
+                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+            "encode_Mpixel_s": px_job / (enc_ms * 1e-3) / 1e6, "decode_Mpixel_s": px_job / (dec_ms * 1e-3) / 1e6,
+            "Mdim_s": value * cfg.xs[0], "bits_per_dim": total_bits / (cfg.xdim * B * world), "roundtrip_ok": roundtrip_ok,
+            "gpu_launches": (launches_enc + launches_dec) * args.steps,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() + bs_bytes),
+                    "d2h_bytes_per_step": int(bs_bytes + out_host.numel()), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "roofline": roofline, "kernels": kernels, "clocks": clocks}
+    if gather_ms is not None:
+        line["bitstream_gather_ms"] = gather_ms
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nimg = args.cpu_baseline_images
+        e, d, bpd = cpu_reference_sample(cfg, nimg)
+        line["cpu_baseline"] = {"value": nimg * 1024 / (e + d) / 1e6, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"one {nimg}-image chain (batch 1), encode then decode; torch-CPU nets with all "
+                                          f"{os.cpu_count()} threads + float64 tables + Python-loop ANS",
+                                "encode_s_per_image": e / nimg, "decode_s_per_image": d / nimg, "bits_per_dim": bpd}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
-    link = [_nvcc(), "-shared", "-o", SO_PATH] + objs + ["-lcuda", "-lcudart"]
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-lcuda"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         raise RuntimeError("link failed:\n" + r.stdout)
@@ -119,6 +119,7 @@ def _set_argtypes(L):
         "bsw_codec_encode": [P, P, I, I, P, I, P],
         "bsw_codec_decode": [P, P, I, I, P, I, P],
         "bsw_codec_last_launches": [P],
+        "bsw_codec_profile": [P, I, P, P],
     }
     for name, args in sig.items():
         fn = getattr(L, name, None)
@@ -126,17 +127,21 @@ def _set_argtypes(L):
             fn.argtypes = args
 
 
-EXPORTS = ["bsw_last_error", "bsw_version", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
+EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
            "bsw_streams_capacity", "bsw_streams_import", "bsw_streams_fill", "bsw_streams_sizes", "bsw_streams_export",
            "bsw_streams_device_ptrs", "bsw_streams_total_words", "bsw_ans_tables", "bsw_ans_push", "bsw_ans_pop",
            "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_bins_create",
            "bsw_bins_destroy", "bsw_bins_device_ptrs", "bsw_gather_zcentres", "bsw_gather_xcentres",
            "bsw_model_create", "bsw_model_destroy", "bsw_model_load_conv", "bsw_model_load_gen_std",
            "bsw_model_finalize", "bsw_vae_infer", "bsw_vae_generate", "bsw_codec_create", "bsw_codec_destroy",
-           "bsw_codec_encode", "bsw_codec_decode", "bsw_codec_last_launches"]
+           "bsw_codec_encode", "bsw_codec_decode", "bsw_codec_last_launches", "bsw_codec_profile"]
 
 
 def cuda_stream_ptr():
     """torch's current CUDA stream as a void* for the `stream` argument of the C ABI."""
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def has_tensor_core_path():
+    return bool(lib().bsw_has_tensor_cores())

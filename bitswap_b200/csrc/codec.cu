@@ -20,6 +20,7 @@ struct bsw_codec {
     std::vector<int16_t *> zs;          // BB-ANS: all nz latents
     uint32_t *priorP, *priorC;          // Logistic(0,1) prior tables over zendpoints[-1], shared by all streams
     int64_t launches;
+    BswProf prof;
 };
 
 // internal int16-symbol variants of the table-driven coder (ans_kernels.cu)
@@ -81,6 +82,16 @@ extern "C" int bsw_codec_destroy(bsw_codec *c) {
 }
 extern "C" int64_t bsw_codec_last_launches(const bsw_codec *c) { return c ? c->launches : 0; }
 
+// Per-category kernel timing for bench.py's roofline (CUDA events on the launching stream).
+extern "C" int bsw_codec_profile(bsw_codec *c, int enable, double *ms_out, int64_t *n_out) {
+    BSW_REQUIRE(c, "null codec");
+    c->prof.collect();
+    if (ms_out) for (int i = 0; i < CAT_COUNT; ++i) ms_out[i] = c->prof.ms[i];
+    if (n_out) for (int i = 0; i < CAT_COUNT; ++i) n_out[i] = c->prof.n[i];
+    if (enable >= 0) { c->prof.reset(); c->prof.on = enable != 0; }
+    return BSW_OK;
+}
+
 #define RC(call) do { if (int rc_ = (call)) return rc_; } while (0)
 
 namespace {
@@ -88,37 +99,67 @@ struct Ctx {
     bsw_codec *c; bsw_streams *s; int first, count; cudaStream_t st;
     int nl = 0;
     const double *zend(int lvl) const { return c->b->zend + (size_t)lvl * c->zdim * c->S; }
-    int infer(int zi) { return bsw_model_run(c->m, true, zi, c->given, count, c->mu, c->scale, 1, st, &nl); }
-    int generate(int zi) { return bsw_model_run(c->m, false, zi, c->given, count, c->mu, c->scale, 0, st, &nl); }
-    int gather_x(const uint8_t *x) { ++nl; return bsw_gather_xcentres(x, c->given, (int64_t)count * c->xdim, st); }
+    int infer(int zi) { return bsw_model_run(c->m, true, zi, c->given, count, c->mu, c->scale, 1, st, &nl, &c->prof); }
+    int generate(int zi) { return bsw_model_run(c->m, false, zi, c->given, count, c->mu, c->scale, 0, st, &nl, &c->prof); }
+    int gather_x(const uint8_t *x) {
+        ++nl;
+        c->prof.begin(CAT_MISC, st);
+        int rc = bsw_gather_xcentres(x, c->given, (int64_t)count * c->xdim, st);
+        c->prof.end(st);
+        return rc;
+    }
     int gather_x16(const int16_t *x);
-    int gather_z(int lvl, const int16_t *sym) { ++nl; return bsw_gather_zcentres(c->b, lvl, sym, c->given, count, st); }
+    int gather_z(int lvl, const int16_t *sym) {
+        ++nl;
+        c->prof.begin(CAT_MISC, st);
+        int rc = bsw_gather_zcentres(c->b, lvl, sym, c->given, count, st);
+        c->prof.end(st);
+        return rc;
+    }
     // q(z_{zi+1} | .) / p(z_zi | .) tables over level `lvl` endpoints
     int pop_z(int lvl, int16_t *sym) {
         ++nl;
-        return bsw_logistic_pop(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+        c->prof.begin(CAT_POP_Z, st);
+        int rc = bsw_logistic_pop(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+        c->prof.end(st);
+        return rc;
     }
     int push_z(int lvl, const int16_t *sym) {
         ++nl;
-        return bsw_logistic_push(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+        c->prof.begin(CAT_PUSH_Z, st);
+        int rc = bsw_logistic_push(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+        c->prof.end(st);
+        return rc;
     }
     // p(x | z_1): ImageBins endpoints (one shared row), 8-bit quantisation (cifar_compress.py:202)
     int64_t xss() const { return c->m->d.cond_xscale ? c->xdim : 0; }
     int pop_x(int16_t *sym) {
         ++nl;
-        return bsw_logistic_pop(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+        c->prof.begin(CAT_POP_X, st);
+        int rc = bsw_logistic_pop(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+        c->prof.end(st);
+        return rc;
     }
     int push_x(const int16_t *sym) {
         ++nl;
-        return bsw_logistic_push(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+        c->prof.begin(CAT_PUSH_X, st);
+        int rc = bsw_logistic_push(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+        c->prof.end(st);
+        return rc;
     }
     int push_prior(const int16_t *sym) {
         ++nl;
-        return bsw_ans_push_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
+        c->prof.begin(CAT_PRIOR, st);
+        int rc = bsw_ans_push_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
+        c->prof.end(st);
+        return rc;
     }
     int pop_prior(int16_t *sym) {
         ++nl;
-        return bsw_ans_pop_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
+        c->prof.begin(CAT_PRIOR, st);
+        int rc = bsw_ans_pop_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
+        c->prof.end(st);
+        return rc;
     }
 };
 __global__ void k_gather_x16(const int16_t *__restrict__ x, float *__restrict__ out, int64_t n) {

@@ -3,6 +3,8 @@
 #include "bsw_common.cuh"
 #include "nets.cuh"
 
+extern "C" int bsw_has_tensor_cores(void) { return 0; }
+
 int bsw_model_tc_prepare(bsw_model *m) {
     (void)m;
     bsw_set_error("use_tensor_cores=1: the tcgen05 conv path is not available in this build");

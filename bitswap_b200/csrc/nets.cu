@@ -428,7 +428,9 @@ __global__ void k_broadcast_rows(const float *__restrict__ src, float *__restric
 }
 
 static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t n, float *mu, float *scale,
-                   cudaStream_t st, int *launches) {
+                   cudaStream_t st, int *launches, BswProf *prof) {
+    BswProf noprof;
+    if (!prof) prof = &noprof;
     BSW_REQUIRE(m->finalized, "model not finalized");
     BSW_REQUIRE(n >= 1 && n <= m->d.max_batch, "batch exceeds the model's max_batch");
     const int Wp = m->Wp;
@@ -440,7 +442,9 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
         a.in = given; a.in_mode = np.in_mode; a.in_dim = np.in_dim; a.Cin = c.Cin; a.CinP = c.CinP; a.ld_in = 0;
         a.w = c.w; a.bias = c.bias; a.CoutP = c.CoutP;
         a.out_mode = OUT_NHWC; a.T = T; a.T_elu = 1; a.A = has_blocks ? A : nullptr; a.A_elu = 1;
+        prof->begin(CAT_CONV_IN, st);
         if (int rc = bsw_conv_simt(a, c.ks, n, st)) return rc;
+        prof->end(st);
         ++*launches;
     }
     for (size_t bi = 0; bi < np.blocks.size(); ++bi) {
@@ -460,9 +464,11 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
                     a.A = (last_layer && last_block) ? nullptr : A; a.A_elu = 1;
                 }
                 int rc;
+                prof->begin(c.ks == 5 ? CAT_CONV_DENSE5 : CAT_CONV_DENSE3, st);
                 if (m->d.use_tensor_cores && m->tc_ready) rc = bsw_conv_tc(m, c, a, n, st);
                 else rc = bsw_conv_simt(a, c.ks, n, st);
                 if (rc) return rc;
+                prof->end(st);
                 ++*launches;
             }
         }
@@ -474,25 +480,29 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
         a.w = c.w; a.bias = c.bias; a.CoutP = c.CoutP;
         a.out_mode = np.out_mode; a.mu = mu; a.scale = scale; a.n_mu = np.n_mu; a.n_sc = np.n_sc;
         a.scale_kind = np.scale_kind; a.out_dim = np.out_dim;
+        prof->begin(CAT_CONV_HEAD, st);
         if (int rc = bsw_conv_simt(a, c.ks, n, st)) return rc;
+        prof->end(st);
         ++*launches;
     }
     return BSW_OK;
 }
 
 int bsw_model_run(bsw_model *m, bool infer, int level, const float *given, int64_t n, float *mu, float *scale,
-                  int scale_per_stream, cudaStream_t st, int *launches) {
+                  int scale_per_stream, cudaStream_t st, int *launches, BswProf *prof) {
     BSW_REQUIRE(m && given && mu, "bsw_vae: null argument");
     BSW_REQUIRE(level >= 0 && level < m->d.nz, "bsw_vae: level out of range");
     const NetPlan &np = infer ? m->infer[level] : m->gen[level];
     int dummy = 0;
     if (!launches) launches = &dummy;
     BSW_REQUIRE(scale || np.n_sc == 0, "bsw_vae: scale output required");
-    if (int rc = run_net(m, np, given, n, mu, scale, st, launches)) return rc;
+    if (int rc = run_net(m, np, given, n, mu, scale, st, launches, prof)) return rc;
     if (!infer && level == 0 && !m->d.cond_xscale && scale) {
         int64_t rows = scale_per_stream ? n : 1;
+        if (prof) prof->begin(CAT_MISC, st);
         k_broadcast_rows<<<(unsigned)((rows * m->xdim + 255) / 256), 256, 0, st>>>(m->xscale, scale, m->xdim, rows);
         BSW_LAUNCH_CHECK();
+        if (prof) prof->end(st);
         ++*launches;
     }
     return BSW_OK;

@@ -57,9 +57,46 @@ struct bsw_model {
     void *tc_state = nullptr;        // owned by conv_tc.cu
 };
 
+// Per-kernel-category device timing (CUDA events on the launching stream), used by bench.py's roofline.
+enum { CAT_MISC = 0, CAT_CONV_IN = 1, CAT_CONV_DENSE3 = 2, CAT_CONV_DENSE5 = 3, CAT_CONV_HEAD = 4, CAT_POP_Z = 5,
+       CAT_PUSH_Z = 6, CAT_POP_X = 7, CAT_PUSH_X = 8, CAT_PRIOR = 9, CAT_COUNT = 10 };
+struct BswProf {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> cats;          // category of event pair i (events 2i, 2i+1)
+    size_t used = 0;
+    double ms[CAT_COUNT] = {0};
+    int64_t n[CAT_COUNT] = {0};
+    void begin(int cat, cudaStream_t st) {
+        if (!on) return;
+        if (used + 2 > pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            pool.push_back(a); pool.push_back(b);
+        }
+        cats.push_back(cat);
+        cudaEventRecord(pool[used], st);
+    }
+    void end(cudaStream_t st) {
+        if (!on) return;
+        cudaEventRecord(pool[used + 1], st);
+        used += 2;
+    }
+    void collect() {          // synchronises on the last event
+        if (used) cudaEventSynchronize(pool[used - 1]);
+        for (size_t i = 0; i < used / 2; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, pool[2 * i], pool[2 * i + 1]);
+            ms[cats[i]] += t; n[cats[i]] += 1;
+        }
+        used = 0; cats.clear();
+    }
+    void reset() { collect(); for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0; n[i] = 0; } }
+};
+
 int bsw_conv_simt(const ConvArgs &a, int ks, int64_t n, cudaStream_t st);
 int bsw_model_run(bsw_model *m, bool infer, int level, const float *given, int64_t n, float *mu, float *scale,
-                  int scale_per_stream, cudaStream_t st, int *launches);
+                  int scale_per_stream, cudaStream_t st, int *launches, BswProf *prof = nullptr);
 // conv_tc.cu
 int bsw_model_tc_prepare(bsw_model *m);
 void bsw_model_tc_release(bsw_model *m);

@@ -48,6 +48,14 @@ class StreamSet:
             heads[i] = st[-1]
         check(lib().bsw_streams_import(self._h, first, len(states), words.ctypes.data, offs.ctypes.data, heads.ctypes.data))
 
+    def import_packed(self, words, offsets, heads, first=0):
+        """Inverse of export(): packed uint32 words + int64 offsets [count+1] + uint64 heads."""
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        heads = np.ascontiguousarray(heads, dtype=np.uint64)
+        wp = words.ctypes.data if words.size else None
+        check(lib().bsw_streams_import(self._h, first, len(heads), wp, offsets.ctypes.data, heads.ctypes.data))
+
     def sizes(self):
         """(nwords int64[B], heads uint64[B], flags int32[B]) -- synchronises."""
         n = np.zeros(self.n, dtype=np.int64)

@@ -36,6 +36,8 @@ typedef enum {
 
 const char *bsw_last_error(void);
 int         bsw_version(void);
+/* 1 if this build contains the tcgen05 conv path (bsw_model_desc.use_tensor_cores may be set). */
+int         bsw_has_tensor_cores(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Stream sets: B device-resident ANS states.
@@ -209,6 +211,10 @@ int bsw_codec_decode(bsw_codec *c, bsw_streams *s, int first, int count, uint8_t
                      void *stream);
 /* Number of kernel launches the last encode/decode call enqueued (bench.py's gpu_launches). */
 int64_t bsw_codec_last_launches(const bsw_codec *c);
+/* Per-kernel-category device time (CUDA events on the launching stream) accumulated since profiling was
+ * enabled.  ms_out/n_out: 10 entries {misc, conv_in, conv_dense3x3, conv_dense5x5, conv_head, pop_z, push_z,
+ * pop_x, push_x, prior}.  enable: 1 = reset and start, 0 = reset and stop, -1 = read only.  Synchronises. */
+int bsw_codec_profile(bsw_codec *c, int enable, double *ms_out, int64_t *n_out);
 
 #ifdef __cplusplus
 }
