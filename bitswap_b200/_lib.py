@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
-    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-lcuda"]
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         raise RuntimeError("link failed:\n" + r.stdout)

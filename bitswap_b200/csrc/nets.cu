@@ -435,6 +435,7 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
     BSW_REQUIRE(n >= 1 && n <= m->d.max_batch, "batch exceeds the model's max_batch");
     const int Wp = m->Wp;
     const bool has_blocks = !np.blocks.empty();
+    const bool use_tc = m->d.use_tensor_cores && m->tc_ready;
     float *T = m->bufT, *A = m->bufA, *B = m->bufB;
     {   // in-conv
         const ConvSlot &c = m->convs[np.in_conv];
@@ -444,6 +445,10 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
         a.out_mode = OUT_NHWC; a.T = T; a.T_elu = 1; a.A = has_blocks ? A : nullptr; a.A_elu = 1;
         prof->begin(CAT_CONV_IN, st);
         if (int rc = bsw_conv_simt(a, c.ks, n, st)) return rc;
+        if (use_tc && has_blocks) {          // conv-input planes for the tensor-core layers: A -> bf16 hi/lo
+            if (int rc = bsw_tc_split(m, A, 0, n, st)) return rc;
+            ++*launches;
+        }
         prof->end(st);
         ++*launches;
     }
@@ -459,13 +464,15 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
                 a.w = c.w; a.bias = c.bias; a.CoutP = c.CoutP; a.out_mode = OUT_NHWC;
                 if (half == 0) {            // conv1: A -> B = ELU(raw)
                     a.in = A; a.A = B; a.A_elu = 1; a.T = nullptr; a.T_elu = 0;
+                    a.in_planes = 0; a.A_planes = 1;
                 } else {                    // conv2: B -> trunk (+ residual), next input into A
                     a.in = B; a.resid = T; a.T = T; a.T_elu = last_layer ? 1 : 0;
                     a.A = (last_layer && last_block) ? nullptr : A; a.A_elu = 1;
+                    a.in_planes = 1; a.A_planes = (last_layer && last_block) ? -1 : 0;
                 }
                 int rc;
                 prof->begin(c.ks == 5 ? CAT_CONV_DENSE5 : CAT_CONV_DENSE3, st);
-                if (m->d.use_tensor_cores && m->tc_ready) rc = bsw_conv_tc(m, c, a, n, st);
+                if (use_tc) rc = bsw_conv_tc(m, c, a, n, st);
                 else rc = bsw_conv_simt(a, c.ks, n, st);
                 if (rc) return rc;
                 prof->end(st);

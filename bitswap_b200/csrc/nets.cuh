@@ -21,6 +21,8 @@ struct ConvArgs {
     const float *resid;
     float *T, *A;
     int T_elu, A_elu;
+    // tensor-core path: index (0/1) of the bf16 hi/lo plane buffer read / written as the conv input (-1: none)
+    int in_planes, A_planes;
     // head epilogue
     float *mu, *scale;
     int n_mu, n_sc, scale_kind, out_dim;
@@ -55,6 +57,7 @@ struct bsw_model {
     bool have_gen_std, finalized;
     bool tc_ready = false;
     void *tc_state = nullptr;        // owned by conv_tc.cu
+    void *tc_slots = nullptr;
 };
 
 // Per-kernel-category device timing (CUDA events on the launching stream), used by bench.py's roofline.
@@ -101,3 +104,4 @@ int bsw_model_run(bsw_model *m, bool infer, int level, const float *given, int64
 int bsw_model_tc_prepare(bsw_model *m);
 void bsw_model_tc_release(bsw_model *m);
 int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st);
+int bsw_tc_split(bsw_model *m, const float *in, int which, int64_t n, cudaStream_t st);

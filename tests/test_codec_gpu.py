@@ -180,3 +180,71 @@ def test_p4_roundtrip_sub_range_and_chain_independence():
     assert ss2.export_lists()[0] == after[4]
     out = codec.decode(ss, 4, first=2)
     assert np.array_equal(out.cpu().numpy(), imgs) and ss.export_lists() == init
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05 path (conv_tc.cu): bf16 hi/lo split, three MMAs per k-block, float32 TMEM accumulation
+# ---------------------------------------------------------------------------------------------------
+from bitswap_b200.config import CodecConfig          # noqa: E402
+
+
+def _tc_case(cfg, B, seed=4):
+    sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=True)
+    m_tc = Model.from_config(cfg, max_batch=B, use_tensor_cores=True).load_state_dict(sd)
+    m_si = Model.from_config(cfg, max_batch=B, use_tensor_cores=False).load_state_dict(sd)
+    m_tc.compress(); m_si.compress()
+    orc = O.ModelOracle(cfg, sd)
+    rs = np.random.RandomState(seed)
+    worst_o = worst_s = 0.0
+    for i in range(cfg.nz):
+        gx = torch.from_numpy((rs.randint(0, 256, (B, cfg.xdim)) - 127.5) / 127.5) if i == 0 else \
+            torch.from_numpy(rs.uniform(-5, 5, (B, cfg.zdim)))
+        gz = torch.from_numpy(rs.uniform(-5, 5, (B, cfg.zdim)))
+        for kind, g in (("infer", gx), ("generate", gz)):
+            f = lambda mm: (mm.infer(i) if kind == "infer" else mm.generate(i))     # noqa: E731
+            mu, sc = f(m_tc)(g.cuda())
+            mu_s, sc_s = f(m_si)(g.cuda())
+            mu_o, sc_o = f(orc)(g)
+            worst_o = max(worst_o, (mu.cpu() - mu_o).abs().max().item(), (sc.cpu() - sc_o).abs().max().item())
+            worst_s = max(worst_s, (mu - mu_s).abs().max().item(), (sc - sc_s).abs().max().item())
+            mu1, sc1 = f(m_tc)(g[B - 1:].cuda())           # batch invariance: last row alone, bit-identical
+            assert torch.equal(mu1[0], mu[B - 1]) and torch.equal(sc1[0], sc[B - 1])
+    return worst_o, worst_s
+
+
+@pytest.mark.parametrize("label,cfg", [
+    ("one 3x3 layer", CodecConfig(xs=(3, 32, 32), nz=1, zchannels=8, nprocessing=0, resdepth=1, reswidth=252)),
+    ("one 5x5 layer", CodecConfig(xs=(3, 32, 32), nz=1, zchannels=8, nprocessing=1, resdepth=0, reswidth=252)),
+    ("width 256 crop", CodecConfig(xs=(3, 32, 32), nz=2, zchannels=8, nprocessing=1, resdepth=2, reswidth=256, cond_xscale=True)),
+])
+def test_p3_tc_single_layers(label, cfg):
+    worst_o, worst_s = _tc_case(cfg, 3)
+    print(f"tcgen05 {label}: max |err| vs torch-f32 oracle {worst_o:.2e}, vs SIMT f32 path {worst_s:.2e}")
+    assert worst_o < TOL and worst_s < TOL
+
+
+def test_p3_tc_cifar8_full():
+    cfg = preset("cifar8")
+    worst_o, worst_s = _tc_case(cfg, 2)
+    print(f"tcgen05 cifar8: max |err| vs torch-f32 oracle {worst_o:.2e}, vs SIMT f32 path {worst_s:.2e}")
+    assert worst_o < TOL and worst_s < TOL
+
+
+def test_p4_tc_roundtrip_cifar8():
+    """Encoder and decoder regenerate bit-identical tables from the tensor-core nets: exact round trip, with a
+    different batch split on the decode side (H3: results do not depend on batch size or position)."""
+    B = 6
+    cfg, m, sd, zend, zcen, codec, ss = _setup("cifar8", B, 8192, tc=True)
+    w, head = synthetic.initial_words(4096, seed=100)
+    ss.fill(w, head)
+    init = ss.export_lists()
+    imgs = synthetic.synthetic_images(cfg, B, seed=21)
+    codec.encode(ss, torch.from_numpy(imgs).cuda())
+    ss.raise_on_error()
+    n, _, _ = ss.sizes()
+    print("cifar8 tcgen05: net bits/dim", 32.0 * (n.mean() - 4095) / cfg.xdim)
+    out_a = codec.decode(ss, 2, first=0)                  # decode in two differently-sized calls
+    out_b = codec.decode(ss, 4, first=2)
+    ss.raise_on_error()
+    assert np.array_equal(torch.cat([out_a, out_b]).cpu().numpy(), imgs)
+    assert ss.export_lists() == init
