@@ -5,15 +5,17 @@
 // model's FLOPs.
 //
 // GEMM view (per image):  D[p, o] = sum_{tap, c} A_tap[p, c] * W[tap][o, c]
-//     M = 256 pixels of one 16x16 image (two UMMA M=128 halves), N = 256 output channels,
-//     K = taps x 256 input channels, walked as (tap, 32-channel chunk) k-blocks.
+//     M = 256 pixels of one 16x16 image (two UMMA M=128 halves), N = 128 output channels per CTA
+//     (grid = images x 2), K = taps x 256 input channels, walked as (tap, 32-channel chunk) k-blocks.
 //   * A_tap is never materialised (no im2col): the activation tensor is NHWC bf16 and one 4-D TMA box
 //     {32 ch, 16 w, 16 h, 1 img} at coordinates (c0, dx-r, dy-r, img) IS the shifted tile; TMA's
 //     out-of-bounds zero fill supplies the "same" padding.
 //   * float32 accuracy on bf16 tensor cores: every operand is split x = hi + lo (two bf16 planes) and
-//     each k-block issues three MMAs  hi*hi + hi*lo + lo*hi  into the same float32 TMEM accumulator
-//     (measured error vs torch float32 through the deepest stack: 3.6e-5, tests/test_codec_gpu.py).
-//   * one CTA per image, accumulators = 2 x (128 lanes x 256 columns) = all 512 TMEM columns.
+//     each k-block issues three MMAs: hi*hi into a MAIN float32 TMEM accumulator, hi*lo and lo*hi into a
+//     separate CROSS accumulator.  The tensor core truncates (RZ) on every accumulate; keeping the 2^-8
+//     smaller cross terms out of the main accumulator cuts its truncating adds 3x (measured: one shared
+//     accumulator gave 1.9e-4 max error through the deepest stack, above the 1e-4 bar).
+//   * accumulators = {main, cross} x 2 halves x (128 lanes x 128 columns) = all 512 TMEM columns.
 //   * warp roles: warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane) and
 //     TMEM allocator, warps 2..9 = epilogue (tcgen05.ld -> bias / residual / ELU / bf16 split -> HBM).
 //   * fixed k order, no split-K, no atomics: results are bit-identical for any batch size or position
@@ -29,9 +31,11 @@ extern "C" int bsw_has_tensor_cores(void) { return 1; }
 namespace {
 
 constexpr int BK = 32;                      // channels per k-block (64-byte rows, SWIZZLE_64B)
-constexpr int NSTAGE = 3;
-constexpr int TILE_BYTES = 256 * BK * 2;    // one 256-row x 32-col bf16 tile = 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES; // A_hi, A_lo, B_hi, B_lo
+constexpr int NSTAGE = 4;
+constexpr int BN = 128;                     // output channels per CTA
+constexpr int TILE_BYTES = 256 * BK * 2;    // one 256-row x 32-col bf16 A tile = 16 KB
+constexpr int WTILE_BYTES = BN * BK * 2;    // one 128-row weight tile = 8 KB
+constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * WTILE_BYTES; // A_hi, A_lo, B_hi, B_lo = 48 KB
 constexpr int TC_THREADS = 320;             // 10 warps
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -93,7 +97,7 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
 }
 // kind::f16 instruction descriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
@@ -142,7 +146,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
     uint32_t *tmem_ptr = (uint32_t *)(acc_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int img = blockIdx.x;
+    const int img = blockIdx.x, co0 = blockIdx.y * BN;
     const int nkb = a.taps * (256 / BK);
 
     if (warp == 0 && lane == 0) {
@@ -176,8 +180,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                 tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img);
                 tma_load_4d(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img);
-                tma_load_3d(st + 2 * TILE_BYTES, &wmap_hi, &full_bar[stage], c0, 0, tap);
-                tma_load_3d(st + 3 * TILE_BYTES, &wmap_lo, &full_bar[stage], c0, 0, tap);
+                tma_load_3d(st + 2 * TILE_BYTES, &wmap_hi, &full_bar[stage], c0, co0, tap);
+                tma_load_3d(st + 2 * TILE_BYTES + WTILE_BYTES, &wmap_lo, &full_bar[stage], c0, co0, tap);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
@@ -197,11 +201,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
                         uint64_t a_hi = make_desc_sw64(sbase + aoff);
                         uint64_t a_lo = make_desc_sw64(sbase + TILE_BYTES + aoff);
                         uint64_t b_hi = make_desc_sw64(sbase + 2 * TILE_BYTES + kk * 32);
-                        uint64_t b_lo = make_desc_sw64(sbase + 3 * TILE_BYTES + kk * 32);
-                        uint32_t d = tmem_base + half * 256;
-                        umma_bf16(d, a_lo, b_hi, (kb | kk) != 0);                   // small terms first
-                        umma_bf16(d, a_hi, b_lo, 1);
-                        umma_bf16(d, a_hi, b_hi, 1);
+                        uint64_t b_lo = make_desc_sw64(sbase + 2 * TILE_BYTES + WTILE_BYTES + kk * 32);
+                        uint32_t d_main = tmem_base + half * BN, d_cross = tmem_base + 256 + half * BN;
+                        umma_bf16(d_main, a_hi, b_hi, (kb | kk) != 0);
+                        umma_bf16(d_cross, a_lo, b_hi, (kb | kk) != 0);
+                        umma_bf16(d_cross, a_hi, b_lo, 1);
                     }
                 }
                 umma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
@@ -219,12 +223,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
         tc_fence_after();
         const int64_t row = ((int64_t)img * 256 + p) * 256;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-            uint32_t rr[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * 256 + c0, rr);
+        for (int cc = 0; cc < BN; cc += 32) {
+            const int c0 = co0 + cc;
+            uint32_t rr[32], rc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN + cc, rr);
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + 256 + half * BN + cc, rc);
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + __ldg(a.bias + c0 + i);
+            for (int i = 0; i < 32; ++i) v[i] = (__uint_as_float(rr[i]) + __uint_as_float(rc[i])) + __ldg(a.bias + c0 + i);
             if (a.resid) {
                 const float4 *rp = reinterpret_cast<const float4 *>(a.resid + row + c0);
 #pragma unroll
@@ -354,7 +360,7 @@ int bsw_model_tc_prepare(bsw_model *m) {
         TcSlot s;
         cuuint64_t dims[3] = {256, 256, (cuuint64_t)taps};
         cuuint64_t str[2] = {256 * 2, 256 * 256 * 2};
-        cuuint32_t box[3] = {BK, 256, 1};
+        cuuint32_t box[3] = {BK, BN, 1};
         if (int rc = encode_map(&s.map_hi, c.w_hi, 3, dims, str, box)) return rc;
         if (int rc = encode_map(&s.map_lo, c.w_lo, 3, dims, str, box)) return rc;
         c.tc_index = (int)slots->size();
@@ -404,7 +410,7 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
-    k_conv_tc<<<(unsigned)n, TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1], s.map_hi,
+    k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1], s.map_hi,
                                                            s.map_lo, t);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
