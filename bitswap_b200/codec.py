@@ -76,12 +76,16 @@ class BitSwapCodec:
         return int(lib().bsw_codec_last_launches(self._h))
 
     CATEGORIES = ("misc", "conv_in", "conv_dense3x3", "conv_dense5x5", "conv_head", "pop_z", "push_z", "pop_x",
-                  "push_x", "prior")
+                  "push_x", "prior", "rows_z", "rows_x")
+
+    def set_two_phase(self, on=True):
+        """True (default): parallel row-table kernel + serial coder; False: fused one-warp-per-stream kernels."""
+        check(lib().bsw_codec_set_two_phase(self._h, int(on)))
 
     def profile(self, enable=-1):
         """Per-kernel-category device time since profiling was enabled: {name: (ms, launches)}.
         enable: True/False resets and starts/stops, -1 just reads."""
-        ms = np.zeros(10, dtype=np.float64)
-        n = np.zeros(10, dtype=np.int64)
+        ms = np.zeros(12, dtype=np.float64)
+        n = np.zeros(12, dtype=np.int64)
         check(lib().bsw_codec_profile(self._h, int(enable), ms.ctypes.data, n.ctypes.data))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.CATEGORIES)}

@@ -1,0 +1,284 @@
+// Two-phase logistic coder (sm_100a): the throughput path of the device-resident codec.
+//
+// The fused kernels of ans_kernels.cu keep one warp per stream busy with the whole row table, which leaves
+// the FP64 pipe 27 % utilised at 1024 streams (profiles/r1_ncu_logistic_pop_v1.md: 7 warps per SM, long
+// dependent DFMA chains).  The table of a row does not depend on the ANS head, only the *search* does, so:
+//
+//   phase A  (k_rows_push / k_rows_pop)   one warp per (stream,row), fully parallel over count x L rows:
+//            float64 logistic cdf -> trunc -> remnant at the row argmax (ANS.__init__ semantics,
+//            cifar_compress.py:28-39).  Streaming reductions only, so few registers and high occupancy.
+//            push: emits the (P_s, C_s) pair of the symbol being coded            ->  8 B per row
+//            pop : emits the integer cdf at every 32nd bin ("coarse cdf", 32 x 4 B) and (argmax, remnant)
+//   phase B  (k_push_pairs / k_pop_coarse) one warp per stream, serial in the head as the reference is
+//            (cifar_compress.py:48-67): push consumes the pairs; pop finds the 32-bin chunk containing
+//            m = head & mask in the coarse cdf, recomputes just that chunk's 33 cdf values with the same
+//            float64 function (bit-identical by construction) and finishes the search with a warp scan.
+//
+// Results are bit-identical to the fused kernels (integer sums are associative; the cdf function is shared).
+#include "bsw_common.cuh"
+
+#define FULL 0xffffffffu
+
+namespace {
+
+struct WarpStream2 {          // same state handling as ans_kernels.cu's WarpStream
+    uint32_t *words;
+    uint64_t x;
+    int len, cap, wbase, err;
+    uint32_t wbuf;
+    __device__ __forceinline__ void open(const bsw_streams &sv, int b) {
+        words = sv.words + (int64_t)b * sv.cap; x = sv.heads[b]; len = sv.nwords[b]; cap = (int)sv.cap;
+        err = sv.flags[b]; wbase = -1; wbuf = 0;
+    }
+    __device__ __forceinline__ void close(const bsw_streams &sv, int b, int lane) {
+        if (lane == 0) { sv.heads[b] = x; sv.nwords[b] = len; sv.flags[b] = err; }
+    }
+    __device__ __forceinline__ uint32_t pop_word(int lane) {
+        int idx = len - 1;
+        if (wbase < 0 || idx < wbase) { wbase = idx & ~31; wbuf = words[wbase + lane]; }
+        len = idx;
+        return __shfl_sync(FULL, wbuf, idx - wbase);
+    }
+    __device__ __forceinline__ void push_begin(int lane) {
+        wbase = len & ~31;
+        wbuf = (wbase + lane < len) ? words[wbase + lane] : 0u;
+    }
+    __device__ __forceinline__ void push_word(uint32_t w, int lane) {
+        if (lane == len - wbase) wbuf = w;
+        ++len;
+        if (len - wbase == 32) { words[wbase + lane] = wbuf; wbase += 32; }
+    }
+    __device__ __forceinline__ void push_end(int lane) { if (lane < len - wbase) words[wbase + lane] = wbuf; }
+    __device__ __forceinline__ void encode(uint32_t p, uint32_t c, int bits, int lane) {      // cifar_compress.py:51-54
+        uint64_t lim = ((((uint64_t)1 << 32) >> bits) << 32) * (uint64_t)p;
+        if (x >= lim) {
+            if (len >= cap) { err = BSW_E_OVERFLOW; return; }
+            push_word((uint32_t)x, lane);
+            x >>= 32;
+        }
+        uint64_t qd = x / p;
+        x = (qd << bits) + (x - qd * p) + c;
+    }
+    __device__ __forceinline__ void decode(uint32_t p, uint32_t c, uint32_t m, int bits, int lane) {   // :63-65
+        x = (uint64_t)p * (x >> bits) + m - c;
+        if (x < ((uint64_t)1 << 32)) {
+            if (len <= 0) { err = BSW_E_UNDERFLOW; return; }
+            x = (x << 32) | pop_word(lane);
+        }
+    }
+};
+
+__device__ __forceinline__ void warp_argmax(uint32_t &val, int &idx) {       // first index wins ties (cifar_compress.py:35)
+    for (int o = 16; o; o >>= 1) {
+        uint32_t ov = __shfl_xor_sync(FULL, val, o);
+        int oi = __shfl_xor_sync(FULL, idx, o);
+        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+}
+
+constexpr int RW = 8;        // warps per CTA in phase A
+
+// ---- phase A ----------------------------------------------------------------------------------------------------
+// Bin ownership is interleaved: lane owns bins k = r*32 + lane, r = 0..NB-1, so endpoint loads are coalesced
+// 256-byte lines and chunk r (32 consecutive bins) is exactly one warp-wide step.
+template <int NB, bool POP>
+__global__ void __launch_bounds__(RW * 32) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
+        const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
+        const int16_t *__restrict__ sym, int bits, int q, uint2 *__restrict__ pairs, uint32_t *__restrict__ coarse,
+        uint2 *__restrict__ fix) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = blockIdx.x;                      // row index i within the level
+    const int si = blockIdx.y * RW + warp;               // stream
+    if (si >= count) return;
+    const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];
+    const double rs = __ddiv_rn(1.0, s);
+    const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));
+    const double *e = endp + row * ers;
+    constexpr int S = 32 * NB;
+    int sy = 0;
+    if (!POP) sy = (int)sym[(int64_t)si * L + row];
+
+    uint32_t best = 0, total = 0, below = 0, ps = 0, myT = 0;
+    int bi = 0;
+    double saved = 0.0;                                   // cdf of lane 31 in the previous chunk (0 before bin 0)
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        const int k = r * 32 + lane;
+        double c = bsw_cdf_rcp(__ldg(e + k), m, s, rs);
+        if (r == NB - 1 && lane == 31) c = 1.0;           // last bin: upper cdf is 1 (cifar_compress.py:184)
+        double rot = __shfl_sync(FULL, c, (lane + 31) & 31);
+        double prev = lane == 0 ? saved : rot;
+        saved = rot;
+        uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;      // :29 trunc, :32 +1
+        if (v > best) { best = v; bi = k; }
+        if (POP) {
+            uint32_t T = __reduce_add_sync(FULL, v);      // total of chunk r
+            if (lane == r) myT = T;
+            total += T;
+        } else {
+            total += v;
+            below += (k < sy) ? v : 0u;
+            if (k == sy) ps = v;
+        }
+    }
+    warp_argmax(best, bi);
+    const int64_t out = (int64_t)si * L + row;
+    if (POP) {
+        const uint32_t rem = (1u << bits) - total;        // :35
+        uint32_t incl = myT;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t base = incl - myT + ((lane * 32 > bi) ? rem : 0u);
+        if (lane < NB) coarse[out * NB + lane] = base;
+        if (lane == 0) fix[out] = make_uint2((uint32_t)bi, rem);
+    } else {
+        total = __reduce_add_sync(FULL, total);
+        below = __reduce_add_sync(FULL, below);
+        ps = __shfl_sync(FULL, ps, sy & 31);
+        const uint32_t rem = (1u << bits) - total;
+        if (lane == 0) pairs[out] = make_uint2(ps + (bi == sy ? rem : 0u), below + (bi < sy ? rem : 0u));
+    }
+}
+
+// ---- phase B: push -------------------------------------------------------------------------------------------------
+constexpr int BW = 4;
+__global__ void __launch_bounds__(BW * 32) k_push_pairs(bsw_streams sv, int first, int count, const uint2 *__restrict__ pairs,
+                                                        int64_t L, int bits) {
+    const int lane = threadIdx.x & 31;
+    const int si = blockIdx.x * BW + (threadIdx.x >> 5);
+    if (si >= count) return;
+    const int b = first + si;
+    WarpStream2 ws;
+    ws.open(sv, b);
+    if (ws.err) return;
+    ws.push_begin(lane);
+    const uint2 *pp = pairs + (int64_t)si * L;
+    uint2 nxt = (lane < L) ? __ldg(pp + lane) : make_uint2(1, 0);
+    for (int64_t i0 = 0; i0 < L && !ws.err; i0 += 32) {
+        uint2 cur = nxt;
+        int64_t r = i0 + 32 + lane;
+        if (r < L) nxt = __ldg(pp + r);                   // prefetch the next 32 rows
+        int n = (int)min((int64_t)32, L - i0);
+        for (int j = 0; j < n && !ws.err; ++j)
+            ws.encode(__shfl_sync(FULL, cur.x, j), __shfl_sync(FULL, cur.y, j), bits, lane);
+    }
+    ws.push_end(lane);
+    ws.close(sv, b, lane);
+}
+
+// ---- phase B: pop ----------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(BW * 32) k_pop_coarse(bsw_streams sv, int first, int count, const float *__restrict__ mu,
+        int64_t mss, const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
+        const uint32_t *__restrict__ coarse, const uint2 *__restrict__ fix, int16_t *__restrict__ sym, int64_t L,
+        int bits, int q) {
+    const int lane = threadIdx.x & 31;
+    const int si = blockIdx.x * BW + (threadIdx.x >> 5);
+    if (si >= count) return;
+    const int b = first + si;
+    WarpStream2 ws;
+    ws.open(sv, b);
+    if (ws.err) return;
+    constexpr int S = 32 * NB;
+    const float *mub = mu + (int64_t)si * mss, *scb = sc + (int64_t)si * sss;
+    const uint32_t *cb = coarse + (int64_t)si * L * NB;
+    const uint2 *fb = fix + (int64_t)si * L;
+    int16_t *sy = sym + (int64_t)si * L;
+    const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));
+    const uint32_t mask = (uint32_t)(((uint64_t)1 << bits) - 1);
+
+    float mu_w = 0.f, sc_w = 1.f;
+    uint2 fx_w = make_uint2(0, 0);
+    int my_sym = 0;
+    // coarse cdf of the next row, prefetched (independent of the head)
+    uint32_t base_n = (lane < NB) ? __ldg(cb + (L - 1) * NB + lane) : 0xffffffffu;
+    for (int64_t i = L - 1; i >= 0; --i) {
+        const int j32 = (int)(i & 31);
+        if (j32 == 31 || i == L - 1) {
+            int64_t r = (i & ~(int64_t)31) + lane;
+            mu_w = r < L ? mub[r] : 0.f;
+            sc_w = r < L ? scb[r] : 1.f;
+            fx_w = r < L ? __ldg(fb + r) : make_uint2(0, 0);
+        }
+        const uint32_t base = base_n;
+        if (i > 0) base_n = (lane < NB) ? __ldg(cb + (i - 1) * NB + lane) : 0xffffffffu;
+        const double m_ = (double)__shfl_sync(FULL, mu_w, j32), s_ = (double)__shfl_sync(FULL, sc_w, j32);
+        const int bi = (int)__shfl_sync(FULL, fx_w.x, j32);
+        const uint32_t rem = __shfl_sync(FULL, fx_w.y, j32);
+        const double rs = __ddiv_rn(1.0, s_);
+        const uint32_t mm = (uint32_t)ws.x & mask;                                       // cifar_compress.py:60
+        const int chunk = 31 - __clz(__ballot_sync(FULL, base <= mm));                   // base of lanes >= NB is UINT_MAX
+        const int k = chunk * 32 + lane;
+        const double *e = endp + i * ers;
+        // two independent cdf evaluations per lane (upper and lower endpoint of my bin)
+        double c_hi = (k == S - 1) ? 1.0 : bsw_cdf_rcp(__ldg(e + k), m_, s_, rs);
+        double c_lo = (k == 0) ? 0.0 : bsw_cdf_rcp(__ldg(e + k - 1), m_, s_, rs);
+        uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c_hi, c_lo), mult)) + 1u + (k == bi ? rem : 0u);
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t cex = __shfl_sync(FULL, base, chunk) + incl - v;                  // integer cdf at my bin
+        const int js = 31 - __clz(__ballot_sync(FULL, cex <= mm));                       // :61 searchsorted 'right' - 1
+        const uint32_t ps = __shfl_sync(FULL, v, js), cs = __shfl_sync(FULL, cex, js);
+        if (lane == j32) my_sym = chunk * 32 + js;                                       // :62
+        ws.decode(ps, cs, mm, bits, lane);                                               // :63-65
+        if (j32 == 0 || ws.err) {
+            int64_t r = (i & ~(int64_t)31) + lane;
+            if (r < L && r >= i) sy[r] = (int16_t)my_sym;
+            if (ws.err) break;
+        }
+    }
+    ws.close(sv, b, lane);
+}
+
+template <int NB>
+int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
+                int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int bits, int q, void *scratch,
+                cudaStream_t st) {
+    dim3 grid((unsigned)L, (count + RW - 1) / RW);
+    uint2 *pairs = (uint2 *)scratch;
+    uint32_t *coarse = (uint32_t *)scratch;
+    uint2 *fix = (uint2 *)((uint8_t *)scratch + (size_t)count * L * NB * 4);
+    if (phase == 0) {
+        if (pop) k_rows<NB, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix);
+        else k_rows<NB, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr);
+    } else {
+        if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
+        else k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pairs, L, bits);
+    }
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+
+}  // namespace
+
+// Scratch bytes needed by the two-phase coder for `count` streams of L rows with support S.
+size_t bsw_rows_scratch_bytes(int count, int64_t L, int S) {
+    size_t pop = (size_t)count * L * (S / 32) * 4 + (size_t)count * L * 8;
+    size_t push = (size_t)count * L * 8;
+    return pop > push ? pop : push;
+}
+
+// Two-phase variants of bsw_logistic_push / bsw_logistic_pop (same arguments + caller-provided scratch).
+// phase 0 = the parallel row-table kernel, phase 1 = the serial coder; call both, in order, on one stream.
+int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
+                    int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
+                    void *scratch, cudaStream_t st) {
+    BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B, "stream range out of bounds");
+    BSW_REQUIRE(mu && sc && endp && sym && scratch && L > 0 && L < 65536 * 32, "two-phase coder: bad arguments");
+    BSW_REQUIRE(ers == 0 || ers >= S, "two-phase coder: endpoint rows must hold S doubles (+inf padded)");
+    switch (S) {
+        case 32:   return launch_rows<1>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 64:   return launch_rows<2>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 128:  return launch_rows<4>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 256:  return launch_rows<8>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 512:  return launch_rows<16>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 1024: return launch_rows<32>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+    }
+    bsw_set_error("two-phase coder: support must be one of 32,64,...,1024 (got %d)", S);
+    return BSW_E_INVALID;
+}

@@ -18,6 +18,8 @@ struct bsw_codec {
     int16_t *sym[2];                    // ping-pong latent symbols [max_batch, zdim]
     int16_t *xsym;                      // [max_batch, xdim] pixels as int16 symbols
     std::vector<int16_t *> zs;          // BB-ANS: all nz latents
+    void *scratch;                      // two-phase coder: pairs / coarse cdf of one level
+    int two_phase;                      // 1: ans_rows.cu path (default), 0: fused one-warp-per-stream kernels
     uint32_t *priorP, *priorC;          // Logistic(0,1) prior tables over zendpoints[-1], shared by all streams
     int64_t launches;
     BswProf prof;
@@ -28,6 +30,11 @@ int bsw_ans_push_i16(bsw_streams *s, int first, int count, const uint32_t *P, co
                      const int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
 int bsw_ans_pop_i16(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *C, int64_t pss, int64_t css,
                     int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
+
+size_t bsw_rows_scratch_bytes(int count, int64_t L, int S);
+int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
+                    int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
+                    void *scratch, cudaStream_t st);
 
 __global__ void k_u8_to_i16(const uint8_t *__restrict__ in, int16_t *__restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,6 +61,11 @@ extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int 
     BSW_CUDA(cudaMalloc(&c->sym[1], sizeof(int16_t) * c->zdim * max_batch));
     BSW_CUDA(cudaMalloc(&c->xsym, sizeof(int16_t) * c->xdim * max_batch));
     c->zs.assign(c->nz, nullptr);
+    {
+        size_t a = bsw_rows_scratch_bytes(max_batch, c->zdim, c->S), b2 = bsw_rows_scratch_bytes(max_batch, c->xdim, 256);
+        BSW_CUDA(cudaMalloc(&c->scratch, a > b2 ? a : b2));
+        c->two_phase = 1;
+    }
     // prior tables: Logistic(0,1) over the top level's endpoints, identical for every stream and image
     // (cifar_compress.py:245-247) -> built once, with the same float64 kernel math as every other table.
     BSW_CUDA(cudaMalloc(&c->priorP, sizeof(uint32_t) * (size_t)c->zdim * c->S));
@@ -76,13 +88,20 @@ extern "C" int bsw_codec_destroy(bsw_codec *c) {
     cudaFree(c->given); cudaFree(c->mu); cudaFree(c->scale);
     cudaFree(c->sym[0]); cudaFree(c->sym[1]); cudaFree(c->xsym);
     for (auto p : c->zs) cudaFree(p);
-    cudaFree(c->priorP); cudaFree(c->priorC);
+    cudaFree(c->priorP); cudaFree(c->priorC); cudaFree(c->scratch);
     delete c;
     return BSW_OK;
 }
 extern "C" int64_t bsw_codec_last_launches(const bsw_codec *c) { return c ? c->launches : 0; }
 
 // Per-category kernel timing for bench.py's roofline (CUDA events on the launching stream).
+/* 1 (default): two-phase coder (parallel row tables + serial coder); 0: fused one-warp-per-stream kernels. */
+extern "C" int bsw_codec_set_two_phase(bsw_codec *c, int on) {
+    BSW_REQUIRE(c, "null codec");
+    c->two_phase = on ? 1 : 0;
+    return BSW_OK;
+}
+
 extern "C" int bsw_codec_profile(bsw_codec *c, int enable, double *ms_out, int64_t *n_out) {
     BSW_REQUIRE(c, "null codec");
     c->prof.collect();
@@ -118,32 +137,76 @@ struct Ctx {
     }
     // q(z_{zi+1} | .) / p(z_zi | .) tables over level `lvl` endpoints
     int pop_z(int lvl, int16_t *sym) {
-        ++nl;
+        if (!c->two_phase) {
+            ++nl;
+            c->prof.begin(CAT_POP_Z, st);
+            int rc = bsw_logistic_pop(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+            c->prof.end(st);
+            return rc;
+        }
+        nl += 2;
+        c->prof.begin(CAT_ROWS_Z, st);
+        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
+        c->prof.end(st);
+        if (rc) return rc;
         c->prof.begin(CAT_POP_Z, st);
-        int rc = bsw_logistic_pop(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
         c->prof.end(st);
         return rc;
     }
     int push_z(int lvl, const int16_t *sym) {
-        ++nl;
+        if (!c->two_phase) {
+            ++nl;
+            c->prof.begin(CAT_PUSH_Z, st);
+            int rc = bsw_logistic_push(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+            c->prof.end(st);
+            return rc;
+        }
+        nl += 2;
+        c->prof.begin(CAT_ROWS_Z, st);
+        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
+        c->prof.end(st);
+        if (rc) return rc;
         c->prof.begin(CAT_PUSH_Z, st);
-        int rc = bsw_logistic_push(s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, sym, c->zdim, c->S, 31, c->q, st);
+        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
         c->prof.end(st);
         return rc;
     }
     // p(x | z_1): ImageBins endpoints (one shared row), 8-bit quantisation (cifar_compress.py:202)
     int64_t xss() const { return c->m->d.cond_xscale ? c->xdim : 0; }
     int pop_x(int16_t *sym) {
-        ++nl;
+        if (!c->two_phase) {
+            ++nl;
+            c->prof.begin(CAT_POP_X, st);
+            int rc = bsw_logistic_pop(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+            c->prof.end(st);
+            return rc;
+        }
+        nl += 2;
+        c->prof.begin(CAT_ROWS_X, st);
+        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
+        c->prof.end(st);
+        if (rc) return rc;
         c->prof.begin(CAT_POP_X, st);
-        int rc = bsw_logistic_pop(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
         c->prof.end(st);
         return rc;
     }
     int push_x(const int16_t *sym) {
-        ++nl;
+        if (!c->two_phase) {
+            ++nl;
+            c->prof.begin(CAT_PUSH_X, st);
+            int rc = bsw_logistic_push(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+            c->prof.end(st);
+            return rc;
+        }
+        nl += 2;
+        c->prof.begin(CAT_ROWS_X, st);
+        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
+        c->prof.end(st);
+        if (rc) return rc;
         c->prof.begin(CAT_PUSH_X, st);
-        int rc = bsw_logistic_push(s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, sym, c->xdim, 256, 31, 8, st);
+        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
         c->prof.end(st);
         return rc;
     }

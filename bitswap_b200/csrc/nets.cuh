@@ -62,7 +62,7 @@ struct bsw_model {
 
 // Per-kernel-category device timing (CUDA events on the launching stream), used by bench.py's roofline.
 enum { CAT_MISC = 0, CAT_CONV_IN = 1, CAT_CONV_DENSE3 = 2, CAT_CONV_DENSE5 = 3, CAT_CONV_HEAD = 4, CAT_POP_Z = 5,
-       CAT_PUSH_Z = 6, CAT_POP_X = 7, CAT_PUSH_X = 8, CAT_PRIOR = 9, CAT_COUNT = 10 };
+       CAT_PUSH_Z = 6, CAT_POP_X = 7, CAT_PUSH_X = 8, CAT_PRIOR = 9, CAT_ROWS_Z = 10, CAT_ROWS_X = 11, CAT_COUNT = 12 };
 struct BswProf {
     bool on = false;
     std::vector<cudaEvent_t> pool;

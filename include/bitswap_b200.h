@@ -211,9 +211,12 @@ int bsw_codec_decode(bsw_codec *c, bsw_streams *s, int first, int count, uint8_t
                      void *stream);
 /* Number of kernel launches the last encode/decode call enqueued (bench.py's gpu_launches). */
 int64_t bsw_codec_last_launches(const bsw_codec *c);
+/* Coder variant: 1 (default) = two-phase (ans_rows.cu: fully parallel float64 row tables, then the serial integer
+ * coder), 0 = fused one-warp-per-stream kernels (bsw_logistic_push/pop).  Bit-identical results. */
+int bsw_codec_set_two_phase(bsw_codec *c, int on);
 /* Per-kernel-category device time (CUDA events on the launching stream) accumulated since profiling was
- * enabled.  ms_out/n_out: 10 entries {misc, conv_in, conv_dense3x3, conv_dense5x5, conv_head, pop_z, push_z,
- * pop_x, push_x, prior}.  enable: 1 = reset and start, 0 = reset and stop, -1 = read only.  Synchronises. */
+ * enabled.  ms_out/n_out: 12 entries {misc, conv_in, conv_dense3x3, conv_dense5x5, conv_head, pop_z, push_z,
+ * pop_x, push_x, prior, rows_z, rows_x} (rows_* = phase A of the two-phase coder; pop/push = phase B).  enable: 1 = reset and start, 0 = reset and stop, -1 = read only.  Synchronises. */
 int bsw_codec_profile(bsw_codec *c, int enable, double *ms_out, int64_t *n_out);
 
 #ifdef __cplusplus

@@ -248,3 +248,32 @@ def test_p4_tc_roundtrip_cifar8():
     ss.raise_on_error()
     assert np.array_equal(torch.cat([out_a, out_b]).cpu().numpy(), imgs)
     assert ss.export_lists() == init
+
+
+@pytest.mark.parametrize("name,scheme", [("tiny3", BITSWAP), ("tiny", BBANS), ("mnist2", BITSWAP)])
+def test_two_phase_coder_equals_fused_coder(name, scheme):
+    """ans_rows.cu (parallel row tables + serial coder) and the fused one-warp-per-stream kernels must leave
+    bit-identical streams and symbols."""
+    B = 5
+    cfg, m, sd, zend, zcen, codec, ss = _setup(name, B, 1 << 14)
+    imgs = synthetic.synthetic_images(cfg, B, seed=31)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(5000 + 3 * b, seed=200 + b)
+        states.append([int(v) for v in w] + [head])
+    res = []
+    for two_phase in (True, False):
+        codec.set_two_phase(two_phase)
+        ss.import_lists(states)
+        codec.encode(ss, torch.from_numpy(imgs).cuda(), scheme=scheme)
+        ss.raise_on_error()
+        res.append(ss.export_lists())
+        out = codec.decode(ss, B, scheme=scheme)
+        assert np.array_equal(out.cpu().numpy(), imgs) and ss.export_lists() == states
+    assert res[0] == res[1]
+    # cross: encode with one variant, decode with the other
+    codec.set_two_phase(True)
+    codec.encode(ss, torch.from_numpy(imgs).cuda(), scheme=scheme)
+    codec.set_two_phase(False)
+    out = codec.decode(ss, B, scheme=scheme)
+    assert np.array_equal(out.cpu().numpy(), imgs) and ss.export_lists() == states
