@@ -121,6 +121,7 @@ def _set_argtypes(L):
         "bsw_codec_last_launches": [P],
         "bsw_codec_profile": [P, I, P, P],
         "bsw_codec_set_two_phase": [P, I],
+        "bsw_selftest_cdf": [L64, U64, P, P],
     }
     for name, args in sig.items():
         fn = getattr(L, name, None)
@@ -128,7 +129,7 @@ def _set_argtypes(L):
             fn.argtypes = args
 
 
-EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
+EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure_fp64_peak", "bsw_selftest_cdf", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
            "bsw_streams_capacity", "bsw_streams_import", "bsw_streams_fill", "bsw_streams_sizes", "bsw_streams_export",
            "bsw_streams_device_ptrs", "bsw_streams_total_words", "bsw_ans_tables", "bsw_ans_push", "bsw_ans_pop",
            "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_bins_create",
@@ -142,6 +143,13 @@ def cuda_stream_ptr():
     """torch's current CUDA stream as a void* for the `stream` argument of the C ABI."""
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def measure_fp64_peak():
+    """Peak float64 FMA lanes per second on the current device."""
+    v = ctypes.c_double()
+    check(lib().bsw_measure_fp64_peak(ctypes.byref(v)))
+    return v.value
 
 
 def has_tensor_core_path():

@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(RW * 32) k_rows(int count, int64_t L, const fl
     uint32_t best = 0, total = 0, below = 0, ps = 0, myT = 0;
     int bi = 0;
     double saved = 0.0;                                   // cdf of lane 31 in the previous chunk (0 before bin 0)
-#pragma unroll
+#pragma unroll 4
     for (int r = 0; r < NB; ++r) {
         const int k = r * 32 + lane;
-        double c = bsw_cdf_rcp(__ldg(e + k), m, s, rs);
+        double c = bsw_cdf_fast(__ldg(e + k), m, s, rs);
         if (r == NB - 1 && lane == 31) c = 1.0;           // last bin: upper cdf is 1 (cifar_compress.py:184)
         double rot = __shfl_sync(FULL, c, (lane + 31) & 31);
         double prev = lane == 0 ? saved : rot;
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(BW * 32) k_pop_coarse(bsw_streams sv, int firs
         const int k = chunk * 32 + lane;
         const double *e = endp + i * ers;
         // two independent cdf evaluations per lane (upper and lower endpoint of my bin)
-        double c_hi = (k == S - 1) ? 1.0 : bsw_cdf_rcp(__ldg(e + k), m_, s_, rs);
-        double c_lo = (k == 0) ? 0.0 : bsw_cdf_rcp(__ldg(e + k - 1), m_, s_, rs);
+        double c_hi = (k == S - 1) ? 1.0 : bsw_cdf_fast(__ldg(e + k), m_, s_, rs);
+        double c_lo = (k == 0) ? 0.0 : bsw_cdf_fast(__ldg(e + k - 1), m_, s_, rs);
         uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c_hi, c_lo), mult)) + 1u + (k == bi ? rem : 0u);
         uint32_t incl = v;
         for (int o = 1; o < 32; o <<= 1) {
@@ -281,4 +281,82 @@ int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, c
     }
     bsw_set_error("two-phase coder: support must be one of 32,64,...,1024 (got %d)", S);
     return BSW_E_INVALID;
+}
+
+// ---- FP64 peak microbenchmark (roofline denominator of the row-table kernel; MEASURED_PEAKS.json has no FP64 figure) ----
+__global__ void k_fp64_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3,
+           a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double b = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+extern "C" int bsw_measure_fp64_peak(double *dfma_per_s) {
+    BSW_REQUIRE(dfma_per_s, "null argument");
+    double *d = nullptr;
+    BSW_CUDA(cudaMalloc(&d, 8));
+    int sms = 0;
+    BSW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    const int iters = 20000, threads = 512, blocks = sms * 4;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_fp64_peak<<<blocks, threads>>>(d, 1000);
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        k_fp64_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        BSW_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double rate = (double)blocks * threads * iters * 8 / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *dfma_per_s = best;
+    return BSW_OK;
+}
+
+// ---- self-test: bsw_cdf_fast against the exact bsw_cdf_div on random (endpoint, mu, sigma) incl. far tails ----
+__global__ void k_cdf_selftest(int64_t n, uint64_t seed, unsigned long long *bad, double *worst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = seed + (uint64_t)i * 0x9E3779B97F4A7C15ULL;
+    auto nxt = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (double)(x >> 11) * (1.0 / 9007199254740992.0); };
+    nxt();
+    int mode = (int)(i & 7);
+    float scf = (mode < 4) ? (float)(0.1 + 0.9 * nxt()) : (mode < 6 ? (float)(0.00098 + 0.05 * nxt()) : (float)(0.0009 + 2.0 * nxt()));
+    float muf = (float)((nxt() - 0.5) * (mode < 4 ? 14.0 : 2.2));
+    double e = (nxt() - 0.5) * (mode < 4 ? 14.0 : 2.2);
+    if (mode == 7) e = (double)(float)e;
+    if ((i & 1023) == 0) e = __longlong_as_double(0x7ff0000000000000LL);      // +inf pad
+    double sc = (double)scf, mu = (double)muf, rs = __ddiv_rn(1.0, sc);
+    double a = bsw_cdf_fast(e, mu, sc, rs), b = bsw_cdf_div(e, mu, sc);
+    double t = __ddiv_rn(__dsub_rn(e, mu), sc);
+    bool ok = (a == b) || (fabs(t) >= 690.0 && ((b < 1e-290 && a < 1e-290 && a >= 0.0) || (b == 1.0 && a == 1.0)));
+    if (!ok) {
+        atomicAdd(bad, 1ULL);
+        worst[0] = e; worst[1] = mu; worst[2] = sc; worst[3] = a; worst[4] = b;
+    }
+}
+extern "C" int bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_host, double *example_host) {
+    BSW_REQUIRE(n > 0 && mismatches_host, "bad arguments");
+    unsigned long long *bad = nullptr;
+    double *worst = nullptr;
+    BSW_CUDA(cudaMalloc(&bad, 8));
+    BSW_CUDA(cudaMalloc(&worst, 5 * 8));
+    BSW_CUDA(cudaMemset(bad, 0, 8));
+    BSW_CUDA(cudaMemset(worst, 0, 40));
+    k_cdf_selftest<<<(unsigned)((n + 255) / 256), 256>>>(n, seed, bad, worst);
+    BSW_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    BSW_CUDA(cudaMemcpy(&h, bad, 8, cudaMemcpyDeviceToHost));
+    if (example_host) BSW_CUDA(cudaMemcpy(example_host, worst, 40, cudaMemcpyDeviceToHost));
+    cudaFree(bad); cudaFree(worst);
+    *mismatches_host = (int64_t)h;
+    return BSW_OK;
 }

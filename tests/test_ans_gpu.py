@@ -274,3 +274,13 @@ def test_fused_underflow_flags_stream():
     assert flags.tolist() == [1, 0]
     with pytest.raises(IndexError):
         ss.raise_on_error()
+
+
+def test_cdf_fast_equals_exact():
+    """The lean float64 cdf of the two-phase kernels (hand-inlined libdevice exp + Newton reciprocal, no range
+    branches) against the exact one (IEEE division + exp()) on 2^27 random triples incl. far tails and +inf."""
+    import ctypes
+    bad = ctypes.c_int64(-1)
+    ex = (ctypes.c_double * 5)()
+    check(lib().bsw_selftest_cdf(1 << 27, 12345, ctypes.byref(bad), ex))
+    assert bad.value == 0, f"{bad.value} mismatches, e.g. (e, mu, sigma, fast, exact) = {list(ex)}"
