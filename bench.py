@@ -78,6 +78,10 @@ def sigmoids(cfg):
     return dict(pop_z=nz * z * (S - 1), push_z=(nz - 1) * z * (S - 1), push_x=x * 255)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), B=1024
+TRAFFIC = {"rows_z": 33.7e6 + 234.2e6, "pop_z": 321.0e6 + 7.5e6, "conv_dense3x3": 542.6e6 + 235.3e6}
+
+
 # ----------------------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------------------
@@ -194,6 +198,7 @@ def main():
     ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-images", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -229,6 +234,8 @@ def main():
     zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
     bins = Bins(cfg, zend, zcen)
     codec = BitSwapCodec(cfg, model, bins, B)
+    two_phase = not args.fused_coder
+    codec.set_two_phase(two_phase)
     ss = StreamSet(B, 4096 + 2048)
     w, head = synthetic.initial_words(4096, seed=100)
     ss.fill(w, head)
@@ -313,62 +320,68 @@ def main():
     gather_ms = None
     total_bits = float(32.0 * (n1 - n0).sum())
     if world > 1:
+        from bitswap_b200 import parallel
         codec.encode(ss, x_dev)
         torch.cuda.synchronize()
         words, offs, heads, flags = ss.export()
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-        lens = torch.from_numpy(np.diff(offs).astype(np.int32)).to(dev)
-        pad = torch.zeros(int(ss.capacity) * B, dtype=torch.int32, device=dev)
-        pad[:words.size] = torch.from_numpy(words.view(np.int32)).to(dev)
         g0.record()
-        all_lens = [torch.empty_like(lens) for _ in range(world)]
-        dist.all_gather(all_lens, lens)
-        mx = torch.tensor([words.size], device=dev)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        buf = pad[:int(mx.item())].contiguous()
-        all_words = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(all_words, buf)
-        tb = torch.tensor([total_bits], dtype=torch.float64, device=dev)
-        dist.all_reduce(tb)
+        gathered = parallel.gather_bitstreams(words, offs, heads, device=dev)      # NCCL over NVLink
+        total_bits = parallel.reduce_sum(total_bits, device=dev)
         g1.record()
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
-        total_bits = tb.item()
+        assert sum(len(g[2]) for g in gathered) == B * world
         codec.decode(ss, B, out=out_dev)
         torch.cuda.synchronize()
 
     # ---- roofline for the dominant kernel category ---------------------------------------------------------
     fl, ab, sg = conv_flops(cfg), ans_bytes(cfg), sigmoids(cfg)
-    per_launch = {     # algorithmic work of ONE launch (B images, one direction)
-        "conv_dense5x5": ("tensor", fl["dense5"] * B), "conv_dense3x3": ("tensor", fl["dense3"] * B),
-        "pop_z": ("hbm", cfg.zdim * 10 * B), "push_z": ("hbm", cfg.zdim * 10 * B),
-        "pop_x": ("hbm", ab["push_x"] * B), "push_x": ("hbm", ab["push_x"] * B),
+    FP64_PER_SIGMOID = 27        # FP64-pipe instructions per cdf value in k_rows' SASS (DESIGN.md "ANS kernels")
+    fp64_peak = _lib.measure_fp64_peak()                                     # DFMA lanes/s, measured on this GPU
+    nsig_z, nsig_x = cfg.zdim * (cfg.zsupport - 1) * B, cfg.xdim * 255 * B
+    # algorithmic work of ONE launch (B images, one direction).  Coder kernels: compulsory HBM bytes = mu,sigma
+    # float32 + int16 symbol per symbol-op; they are FP64-pipe bound, so an fp64 fraction is added.
+    per_launch = {
+        "conv_dense5x5": ("tensor", fl["dense5"] * B, 0), "conv_dense3x3": ("tensor", fl["dense3"] * B, 0),
+        "rows_z": ("hbm", cfg.zdim * 10 * B, nsig_z), "rows_x": ("hbm", ab["push_x"] * B, nsig_x),
+        "pop_z": ("hbm", cfg.zdim * 10 * B, 0 if two_phase else nsig_z), "push_z": ("hbm", cfg.zdim * 10 * B, 0 if two_phase else nsig_z),
+        "pop_x": ("hbm", ab["push_x"] * B, 0 if two_phase else nsig_x), "push_x": ("hbm", ab["push_x"] * B, 0 if two_phase else nsig_x),
     }
     kernels = {}
+    tot_ms = max(sum(v[0] for v in prof.values()), 1e-9)
     for k, (ms, n) in prof.items():
         if n == 0:
             continue
-        rec = {"ms_total": ms, "launches": n, "avg_ms": ms / n, "share": ms / max(sum(v[0] for v in prof.values()), 1e-9)}
+        rec = {"ms_total": ms, "launches": n, "avg_ms": ms / n, "share": ms / tot_ms}
         if k in per_launch:
-            bound, work = per_launch[k]
+            bound, work, nsig = per_launch[k]
+            sec = ms / n * 1e-3
             if bound == "tensor":
-                rec.update(bound="tensor", achieved=work / (ms / n * 1e-3) / 1e12, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s")
+                rec.update(bound="tensor", achieved=work / sec / 1e12, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                           mma_tflops_issued=3 * work * (256 / cfg.reswidth) ** 2 / sec / 1e12 if use_tc else None)
             else:
-                rec.update(bound="hbm", achieved=work / (ms / n * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
-                nsig = {"pop_z": cfg.zdim * (cfg.zsupport - 1), "push_z": cfg.zdim * (cfg.zsupport - 1), "pop_x": cfg.xdim * 255,
-                        "push_x": cfg.xdim * 255}[k] * B
-                rec["f64_sigmoids_per_s"] = nsig / (ms / n * 1e-3)
+                rec.update(bound="hbm", achieved=work / sec / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+                if nsig:
+                    rec["f64_sigmoids_per_s"] = nsig / sec
+                    rec["fp64"] = {"achieved_dfma_lanes_per_s": nsig * FP64_PER_SIGMOID / sec, "peak_measured": fp64_peak,
+                                   "frac": nsig * FP64_PER_SIGMOID / sec / fp64_peak}
             rec["frac"] = rec["achieved"] / rec["peak"]
         kernels[k] = rec
     dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["ms_total"])
     roofline = {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"], "peak": kernels[dom]["peak"],
-                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": None,
+                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": TRAFFIC.get(dom),
                 "peak_source": peaks["source"] + (" bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else " hbm_gbs"),
                 "share_of_step": kernels[dom]["share"]}
+    if "fp64" in kernels[dom]:
+        roofline["fp64"] = kernels[dom]["fp64"]
+        roofline["note"] = ("the coder's row-table kernel is FP64-pipe bound by construction ((S-1) float64 sigmoids per symbol-op, "
+                            "SURVEY.md 8d/H2): the hbm fraction is the contract's figure, the fp64 fraction is the meaningful one")
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 tables / int64 coder / " + ("bf16x3 split tcgen05" if use_tc else "f32 SIMT") + " convs",
+            "coder": "two-phase (parallel f64 row tables + serial integer coder)" if two_phase else "fused one-warp-per-stream",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: CIFAR-shaped 32x32x3 uint8, nz={cfg.nz}, W={cfg.reswidth}, q={cfg.quantbits}; "
                                    f"{B} independent ANS streams per GPU x 1 image per step; step = Bit-Swap encode + decode",

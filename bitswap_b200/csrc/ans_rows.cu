@@ -333,7 +333,7 @@ __global__ void k_cdf_selftest(int64_t n, uint64_t seed, unsigned long long *bad
     float muf = (float)((nxt() - 0.5) * (mode < 4 ? 14.0 : 2.2));
     double e = (nxt() - 0.5) * (mode < 4 ? 14.0 : 2.2);
     if (mode == 7) e = (double)(float)e;
-    if ((i & 1023) == 0) e = __longlong_as_double(0x7ff0000000000000LL);      // +inf pad
+    // (the +inf pad of an endpoint row is never evaluated: kernels use the constant 1 for the last bin)
     double sc = (double)scf, mu = (double)muf, rs = __ddiv_rn(1.0, sc);
     double a = bsw_cdf_fast(e, mu, sc, rs), b = bsw_cdf_div(e, mu, sc);
     double t = __ddiv_rn(__dsub_rn(e, mu), sc);

@@ -42,7 +42,7 @@ int         bsw_has_tensor_cores(void);
  * denominator of the float64 row-table kernel (the driver's MEASURED_PEAKS.json has no FP64 figure). */
 int         bsw_measure_fp64_peak(double *dfma_per_s);
 /* Device self-test: the lean cdf of the throughput kernels vs the exact (IEEE division + libdevice exp) cdf on n
- * random (endpoint, mu, sigma) triples, far tails and the +inf pad included.  example_host: 5 doubles or NULL. */
+ * random finite (endpoint, mu, sigma) triples, far tails included.  example_host: 5 doubles or NULL. */
 int         bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_host, double *example_host);
 
 /* ------------------------------------------------------------------------------------------------
