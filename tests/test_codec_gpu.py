@@ -277,3 +277,85 @@ def test_two_phase_coder_equals_fused_coder(name, scheme):
     codec.set_two_phase(False)
     out = codec.decode(ss, B, scheme=scheme)
     assert np.array_equal(out.cpu().numpy(), imgs) and ss.export_lists() == states
+
+
+def test_config0_mnist_b1_state_identical_at_every_level():
+    """BASELINE.json configs[0]: MNIST 32x32x1 (28x28 zero-padded), 2-latent VAE, batch = 1.  The reference's own
+    loop shape (cifar_compress.py:175-250) driven level by level through the drop-in pieces -- model.infer /
+    generate, the fused logistic coder, the prior table -- must leave the ANS state bit-identical to the CPU
+    oracle after EVERY pop and push (oracle fed the same GPU mu/sigma), for a 2-image chain."""
+    import ctypes
+    from bitswap_b200._lib import lib, check, cuda_stream_ptr
+    cfg = preset("mnist2")
+    m, sd = _model(cfg, 1)
+    zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    bins = Bins(cfg, zend, zcen)
+    S, q = cfg.zsupport, cfg.quantbits
+
+    def ptrs(level):
+        a, b, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().bsw_bins_device_ptrs(bins.handle, level, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, c.value
+
+    # oracle trace with the GPU nets injected
+    trace = []
+    orc = O.BitSwapOracle(cfg, O.ModelOracle(cfg, sd), zend, zcen, coder="c", pmf="c", trace=trace)
+
+    def gpu_net(kind, level, given):
+        f = m.infer(level) if kind == "infer" else m.generate(level)
+        mu, sc = f(given.cuda())
+        return mu.cpu(), sc.cpu()
+    orc._net = gpu_net
+    imgs = np.zeros((2, 1, 32, 32), dtype=np.uint8)
+    imgs[:, :, 2:30, 2:30] = synthetic.synthetic_images(cfg, 2, seed=13)[:, :, 2:30, 2:30]     # Pad(2), mnist_compress.py:129
+    w, head = synthetic.initial_words(1500, seed=100)
+    st = O.CState(w, head)
+    for xi in range(2):
+        st = orc.encode_image(st, imgs[xi])
+    want = [(ln, sha) for _, ln, sha in trace]
+
+    ss = StreamSet(1, 1 << 14)
+    ss.fill(w, head)
+    got = []
+
+    def note():
+        lst = ss.export_lists()[0]
+        got.append((len(lst), O.CState.from_list(lst).digest()))
+    zr = torch.arange(cfg.zdim)
+    P = torch.empty((cfg.zdim, S), dtype=torch.int32, device="cuda")
+    C = torch.empty((cfg.zdim, S + 1), dtype=torch.int32, device="cuda")
+    zero, one = torch.zeros(1, dtype=torch.float64, device="cuda"), torch.ones(1, dtype=torch.float64, device="cuda")
+    e_top = zend[-1].contiguous().cuda()
+    check(lib().bsw_logistic_tables(e_top.data_ptr(), S - 1, zero.data_ptr(), one.data_ptr(), 0, cfg.zdim, S, 31, q,
+                                    P.data_ptr(), C.data_ptr(), cuda_stream_ptr()))
+    for xi in range(2):
+        x = torch.from_numpy(imgs[xi].reshape(-1).astype(np.int64))
+        zsym = None
+        for zi in range(cfg.nz):
+            given = zcen[zi - 1, zr, zsym.long().cpu()] if zi > 0 else (x.double() - 127.5) / 127.5
+            mu, sc = m.infer(zi)(given.cuda())
+            mu32, sc32 = mu.float().contiguous(), sc.float().contiguous()
+            out = torch.zeros(cfg.zdim, dtype=torch.int16, device="cuda")
+            ze, xe = ptrs(zi)
+            check(lib().bsw_logistic_pop(ss.handle, 0, 1, mu32.data_ptr(), cfg.zdim, sc32.data_ptr(), cfg.zdim, ze, S,
+                                         out.data_ptr(), cfg.zdim, S, 31, q, cuda_stream_ptr()))
+            note()
+            mu, sc = m.generate(zi)(zcen[zi, zr, out.long().cpu()].cuda())
+            mu32, sc32 = mu.float().contiguous(), sc.float().contiguous()
+            if zi > 0:
+                zl, _ = ptrs(zi - 1)
+                sy = zsym.to(torch.int16).contiguous()
+                check(lib().bsw_logistic_push(ss.handle, 0, 1, mu32.data_ptr(), cfg.zdim, sc32.data_ptr(), cfg.zdim, zl, S,
+                                              sy.data_ptr(), cfg.zdim, S, 31, q, cuda_stream_ptr()))
+            else:
+                sy = x.to(torch.int16).cuda().contiguous()
+                check(lib().bsw_logistic_push(ss.handle, 0, 1, mu32.data_ptr(), cfg.xdim, sc32.data_ptr(), cfg.xdim, xe, 0,
+                                              sy.data_ptr(), cfg.xdim, 256, 31, 8, cuda_stream_ptr()))
+            note()
+            zsym = out
+        s32 = zsym.to(torch.int32).contiguous()
+        check(lib().bsw_ans_push(ss.handle, 0, 1, P.data_ptr(), C.data_ptr(), 0, 0, s32.data_ptr(), cfg.zdim, S, 31,
+                                 cuda_stream_ptr()))
+        note()
+    ss.raise_on_error()
+    assert got == want
