@@ -732,7 +732,9 @@ extern "C" int bsw_bins_create(bsw_bins **out, int nz, int zdim, int q, int xdim
     bsw_bins *b = new bsw_bins();
     b->nz = nz; b->zdim = zdim; b->q = q; b->S = 1 << q; b->xdim = xdim;
     const int S = b->S;
-    const double inf = __builtin_inf();
+    // pad value of every endpoint row: any finite value this large gives cdf == 1.0 exactly in every kernel
+    // (a literal +inf would turn the reciprocal-division shortcut into inf - inf)
+    const double inf = 1e300;
     size_t rows = (size_t)nz * zdim;
     std::vector<double> pad(rows * S);
     for (size_t r = 0; r < rows; ++r) {

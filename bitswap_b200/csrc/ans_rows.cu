@@ -82,7 +82,7 @@ constexpr int RW = 8;        // warps per CTA in phase A
 // Bin ownership is interleaved: lane owns bins k = r*32 + lane, r = 0..NB-1, so endpoint loads are coalesced
 // 256-byte lines and chunk r (32 consecutive bins) is exactly one warp-wide step.
 template <int NB, bool POP>
-__global__ void __launch_bounds__(RW * 32) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
+__global__ void __launch_bounds__(RW * 32, 4) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint2 *__restrict__ pairs, uint32_t *__restrict__ coarse,
         uint2 *__restrict__ fix) {
@@ -94,18 +94,20 @@ __global__ void __launch_bounds__(RW * 32) k_rows(int count, int64_t L, const fl
     const double rs = __ddiv_rn(1.0, s);
     const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));
     const double *e = endp + row * ers;
-    constexpr int S = 32 * NB;
     int sy = 0;
     if (!POP) sy = (int)sym[(int64_t)si * L + row];
 
     uint32_t best = 0, total = 0, below = 0, ps = 0, myT = 0;
     int bi = 0;
+    BswExpRegs K;
+    K.load();
     double saved = 0.0;                                   // cdf of lane 31 in the previous chunk (0 before bin 0)
 #pragma unroll 4
     for (int r = 0; r < NB; ++r) {
         const int k = r * 32 + lane;
-        double c = bsw_cdf_fast(__ldg(e + k), m, s, rs);
-        if (r == NB - 1 && lane == 31) c = 1.0;           // last bin: upper cdf is 1 (cifar_compress.py:184)
+        // the row's last entry is the +1e300 pad: t clamps to +690 and the cdf comes out as exactly 1.0, which is
+        // the reference's `1. - cdfs[:,-1]` upper bound of the last bin (cifar_compress.py:184)
+        double c = bsw_cdf_fast_regs(__ldg(e + k), m, s, rs, K);
         double rot = __shfl_sync(FULL, c, (lane + 31) & 31);
         double prev = lane == 0 ? saved : rot;
         saved = rot;

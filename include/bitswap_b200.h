@@ -140,7 +140,7 @@ int bsw_logistic_pop(bsw_streams *s, int first, int count, const float *mu_dev, 
  * Bin tables on the device.
  * Replaces: the tensors returned by discretize() (discretization.py:9-99) and ImageBins
  * (utils/torch/rand.py:134-153); the library keeps its own padded copy (each endpoint row padded
- * with +inf to S entries so that cdf_{S-1} == 1 falls out of the same formula).
+ * with +1e300 to S entries so that cdf_{S-1} == 1 falls out of the same formula).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct bsw_bins bsw_bins;
 /* zendpoints_host [nz, zdim, S-1], zcentres_host [nz, zdim, S] float64 (reference layout). */
