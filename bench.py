@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-images", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=4, help="sub-batches coded concurrently on separate CUDA streams (1 = off)")
     ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
     args = ap.parse_args()
 
@@ -230,11 +231,15 @@ def main():
     if use_tc < 0:
         use_tc = 1 if (_lib.has_tensor_core_path() and (cfg.reswidth + 63) // 64 * 64 == 256) else 0
     sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=False)          # default-init distribution
-    model = Model.from_config(cfg, max_batch=B, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
-    model.compress()
     zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
     bins = Bins(cfg, zend, zcen)
-    codec = BitSwapCodec(cfg, model, bins, B)
+    if args.lanes > 1:
+        from bitswap_b200.codec import PipelinedCodec
+        codec = PipelinedCodec(cfg, sd, bins, B, lanes=args.lanes, use_tensor_cores=bool(use_tc))
+    else:
+        model = Model.from_config(cfg, max_batch=B, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
+        model.compress()
+        codec = BitSwapCodec(cfg, model, bins, B)
     two_phase = not args.fused_coder
     codec.set_two_phase(two_phase)
     ss = StreamSet(B, 4096 + 2048)
@@ -340,14 +345,15 @@ def main():
     fl, ab, sg = conv_flops(cfg), ans_bytes(cfg), sigmoids(cfg)
     FP64_PER_SIGMOID = 27        # FP64-pipe instructions per cdf value in k_rows' SASS (DESIGN.md "ANS kernels")
     fp64_peak = _lib.measure_fp64_peak()                                     # DFMA lanes/s, measured on this GPU
-    nsig_z, nsig_x = cfg.zdim * (cfg.zsupport - 1) * B, cfg.xdim * 255 * B
+    Bl = B // max(args.lanes, 1) if args.lanes > 1 else B        # images per kernel launch (per lane)
+    nsig_z, nsig_x = cfg.zdim * (cfg.zsupport - 1) * Bl, cfg.xdim * 255 * Bl
     # algorithmic work of ONE launch (B images, one direction).  Coder kernels: compulsory HBM bytes = mu,sigma
     # float32 + int16 symbol per symbol-op; they are FP64-pipe bound, so an fp64 fraction is added.
     per_launch = {
-        "conv_dense5x5": ("tensor", fl["dense5"] * B, 0), "conv_dense3x3": ("tensor", fl["dense3"] * B, 0),
-        "rows_z": ("hbm", cfg.zdim * 10 * B, nsig_z), "rows_x": ("hbm", ab["push_x"] * B, nsig_x),
-        "pop_z": ("hbm", cfg.zdim * 10 * B, 0 if two_phase else nsig_z), "push_z": ("hbm", cfg.zdim * 10 * B, 0 if two_phase else nsig_z),
-        "pop_x": ("hbm", ab["push_x"] * B, 0 if two_phase else nsig_x), "push_x": ("hbm", ab["push_x"] * B, 0 if two_phase else nsig_x),
+        "conv_dense5x5": ("tensor", fl["dense5"] * Bl, 0), "conv_dense3x3": ("tensor", fl["dense3"] * Bl, 0),
+        "rows_z": ("hbm", cfg.zdim * 10 * Bl, nsig_z), "rows_x": ("hbm", ab["push_x"] * Bl, nsig_x),
+        "pop_z": ("hbm", cfg.zdim * 10 * Bl, 0 if two_phase else nsig_z), "push_z": ("hbm", cfg.zdim * 10 * Bl, 0 if two_phase else nsig_z),
+        "pop_x": ("hbm", ab["push_x"] * Bl, 0 if two_phase else nsig_x), "push_x": ("hbm", ab["push_x"] * Bl, 0 if two_phase else nsig_x),
     }
     kernels = {}
     tot_ms = max(sum(v[0] for v in prof.values()), 1e-9)
@@ -371,7 +377,7 @@ def main():
         kernels[k] = rec
     dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["ms_total"])
     roofline = {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"], "peak": kernels[dom]["peak"],
-                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": TRAFFIC.get(dom),
+                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": (TRAFFIC.get(dom) * Bl / 1024 if TRAFFIC.get(dom) else None),
                 "peak_source": peaks["source"] + (" bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else " hbm_gbs"),
                 "share_of_step": kernels[dom]["share"]}
     if "fp64" in kernels[dom]:
@@ -383,13 +389,16 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 tables / int64 coder / " + ("bf16x3 split tcgen05" if use_tc else "f32 SIMT") + " convs",
             "coder": "two-phase (parallel f64 row tables + serial integer coder)" if two_phase else "fused one-warp-per-stream",
+            "lanes": args.lanes,
             "data": "synthetic",
             "config": {"workload": f"{args.config}: CIFAR-shaped 32x32x3 uint8, nz={cfg.nz}, W={cfg.reswidth}, q={cfg.quantbits}; "
                                    f"{B} independent ANS streams per GPU x 1 image per step; step = Bit-Swap encode + decode",
                        "streams_per_gpu": B, "global_batch": B * world, "weights": "seeded random init (reference default-init distribution)",
                        "bins": "synthetic uniform grids + float32 equal-mass top level", "images": "iid uniform uint8",
                        "l2": "per-step working set (3 x 268 MB activations + streams) >> 126 MB L2: no explicit flush needed",
-                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective; within a GPU {args.lanes} sub-batches "
+                                      "on separate CUDA streams so FP64-bound coder kernels and tensor-bound convs overlap "
+                                      "(per-kernel times below are measured under that concurrency)"},
             "encode_Mpixel_s": px_job / (enc_ms * 1e-3) / 1e6, "decode_Mpixel_s": px_job / (dec_ms * 1e-3) / 1e6,
             "Mdim_s": value * cfg.xs[0], "bits_per_dim": total_bits / (cfg.xdim * B * world), "roundtrip_ok": roundtrip_ok,
             "gpu_launches": (launches_enc + launches_dec) * args.steps,

@@ -89,3 +89,70 @@ class BitSwapCodec:
         n = np.zeros(12, dtype=np.int64)
         check(lib().bsw_codec_profile(self._h, int(enable), ms.ctypes.data, n.ctypes.data))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.CATEGORIES)}
+
+
+class PipelinedCodec:
+    """`lanes` BitSwapCodecs, each coding a contiguous sub-range of the streams on its own CUDA stream.
+
+    The coder's row-table kernel is FP64-pipe bound and the dense convs are tensor-pipe bound; chains of
+    different sub-batches drift apart in phase, so their kernels share SMs and the two pipes overlap
+    (measured on B200, C8, 1024 streams: 379 -> 345 ms per encode+decode step with 4 lanes; more lanes do not
+    help).  Results are identical to a single BitSwapCodec: every stream is independent and every kernel is
+    batch-invariant.  Each lane owns a model replica (activations are per-lane anyway)."""
+
+    def __init__(self, cfg: CodecConfig, state_dict, bins: Bins, max_batch: int, lanes: int = 4, use_tensor_cores=True):
+        self.cfg, self.bins, self.max_batch = cfg, bins, int(max_batch)
+        self.lanes = max(1, min(int(lanes), self.max_batch))
+        self.per = -(-self.max_batch // self.lanes)
+        self.models, self.codecs, self.streams = [], [], []
+        for _ in range(self.lanes):
+            m = Model.from_config(cfg, max_batch=self.per, use_tensor_cores=use_tensor_cores).load_state_dict(state_dict)
+            m.compress()
+            self.models.append(m)
+            self.codecs.append(BitSwapCodec(cfg, m, bins, self.per))
+            self.streams.append(torch.cuda.Stream())
+
+    def _ranges(self, count):
+        out, b = [], 0
+        while b < count:
+            out.append((b, min(self.per, count - b)))
+            b += self.per
+        return out
+
+    def _fan(self, count, fn):
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for i, (b, n) in enumerate(self._ranges(count)):
+            st = self.streams[i]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                fn(self.codecs[i], b, n)
+        for i in range(len(self._ranges(count))):
+            cur.wait_stream(self.streams[i])
+
+    def encode(self, streams: StreamSet, x: torch.Tensor, first=0, scheme=BITSWAP):
+        assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.shape[0] <= self.max_batch
+        self._fan(x.shape[0], lambda c, b, n: c.encode(streams, x[b:b + n], first=first + b, scheme=scheme))
+
+    def decode(self, streams: StreamSet, count: int, first=0, scheme=BITSWAP, out=None):
+        if out is None:
+            out = torch.empty((count,) + tuple(self.cfg.xs), dtype=torch.uint8, device="cuda")
+        self._fan(count, lambda c, b, n: c.decode(streams, n, first=first + b, scheme=scheme, out=out[b:b + n]))
+        return out
+
+    def set_two_phase(self, on=True):
+        for c in self.codecs:
+            c.set_two_phase(on)
+
+    @property
+    def last_launches(self):
+        return sum(c.last_launches for c in self.codecs)
+
+    def profile(self, enable=-1):
+        tot = {}
+        for c in self.codecs:
+            for k, (ms, n) in c.profile(enable).items():
+                a = tot.get(k, (0.0, 0))
+                tot[k] = (a[0] + ms, a[1] + n)
+        return tot

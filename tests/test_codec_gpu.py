@@ -359,3 +359,30 @@ def test_config0_mnist_b1_state_identical_at_every_level():
         note()
     ss.raise_on_error()
     assert got == want
+
+
+def test_pipelined_codec_equals_single_codec():
+    """PipelinedCodec (sub-batches on separate CUDA streams) leaves exactly the streams a single codec leaves."""
+    from bitswap_b200.codec import PipelinedCodec
+    B = 7
+    cfg, m, sd, zend, zcen, codec, ss = _setup("tiny3", B, 1 << 14)
+    pc = PipelinedCodec(cfg, sd, Bins(cfg, zend, zcen), B, lanes=3, use_tensor_cores=False)
+    imgs = synthetic.synthetic_images(cfg, 2 * B, seed=41).reshape(2, B, *cfg.xs)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(4000 + b, seed=300 + b)
+        states.append([int(v) for v in w] + [head])
+    res = []
+    for c in (codec, pc):
+        ss.import_lists(states)
+        for xi in range(2):
+            c.encode(ss, torch.from_numpy(imgs[xi]).cuda())
+        torch.cuda.synchronize()
+        ss.raise_on_error()
+        res.append(ss.export_lists())
+    assert res[0] == res[1]
+    for xi in (1, 0):
+        out = pc.decode(ss, B)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), imgs[xi])
+    assert ss.export_lists() == states
