@@ -275,7 +275,8 @@ def main():
         codec.decode(ss, B, out=out_dev)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    codec.profile(True)
+    if args.lanes <= 1:
+        codec.profile(True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     ev[0].record()
     for i in range(args.steps):
@@ -287,8 +288,20 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     enc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
     dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps))
-    prof = codec.profile(False)
     clocks = sampler.stop() if sampler else None
+    if args.lanes > 1:
+        # Per-kernel times: with several lanes in flight the kernels of different lanes share SMs, so event durations
+        # taken inside the timed region overlap each other.  Replay the same steps with the lanes back to back on one
+        # stream (same kernels, same launch shapes) and time each kernel there.
+        codec.serial = True
+        codec.profile(True)
+        for i in range(args.steps):
+            codec.encode(ss, x_dev)
+            codec.decode(ss, B, out=out_dev)
+        prof = codec.profile(False)
+        codec.serial = False
+    else:
+        prof = codec.profile(False)
     barrier()
     t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -404,7 +417,10 @@ def main():
             "gpu_launches": (launches_enc + launches_dec) * args.steps,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() + bs_bytes),
                     "d2h_bytes_per_step": int(bs_bytes + out_host.numel()), "ms_per_step": 1e3 * e2e_s / args.steps},
-            "roofline": roofline, "kernels": kernels, "clocks": clocks}
+            "roofline": roofline, "kernels": kernels, "clocks": clocks,
+            "kernels_timing": ("CUDA events around every launch inside the timed region" if args.lanes <= 1 else
+                               f"CUDA events around every launch in a serial replay of the same {args.steps} steps (lanes back to back on one "
+                               "stream, same kernels and launch shapes); the timed region itself runs the lanes concurrently")}
     if gather_ms is not None:
         line["bitstream_gather_ms"] = gather_ms
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -105,6 +105,7 @@ class PipelinedCodec:
         self.lanes = max(1, min(int(lanes), self.max_batch))
         self.per = -(-self.max_batch // self.lanes)
         self.models, self.codecs, self.streams = [], [], []
+        self.serial = False          # True: run the lanes back to back on the current stream (clean per-kernel timing)
         for _ in range(self.lanes):
             m = Model.from_config(cfg, max_batch=self.per, use_tensor_cores=use_tensor_cores).load_state_dict(state_dict)
             m.compress()
@@ -120,6 +121,10 @@ class PipelinedCodec:
         return out
 
     def _fan(self, count, fn):
+        if self.serial:
+            for i, (b, n) in enumerate(self._ranges(count)):
+                fn(self.codecs[i], b, n)
+            return
         cur = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(cur)
