@@ -290,16 +290,24 @@ def main():
     dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps))
     clocks = sampler.stop() if sampler else None
     if args.lanes > 1:
-        # Per-kernel times: with several lanes in flight the kernels of different lanes share SMs, so event durations
-        # taken inside the timed region overlap each other.  Replay the same steps with the lanes back to back on one
-        # stream (same kernels, same launch shapes) and time each kernel there.
-        codec.serial = True
-        codec.profile(True)
+        # Per-kernel times.  With several lanes in flight the kernels of different lanes share SMs, so event durations
+        # taken inside the timed region overlap each other and cannot be attributed.  The same steps are therefore
+        # replayed on ONE stream by a single-lane codec at the full batch (same kernels; launch shape = B images instead
+        # of B/lanes) with CUDA events around every launch.
+        model1 = Model.from_config(cfg, max_batch=B, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
+        model1.compress()
+        codec1 = BitSwapCodec(cfg, model1, bins, B)
+        codec1.set_two_phase(two_phase)
+        for _ in range(2):
+            codec1.encode(ss, x_dev)
+            codec1.decode(ss, B, out=out_dev)
+        codec1.profile(True)
         for i in range(args.steps):
-            codec.encode(ss, x_dev)
-            codec.decode(ss, B, out=out_dev)
-        prof = codec.profile(False)
-        codec.serial = False
+            codec1.encode(ss, x_dev)
+            codec1.decode(ss, B, out=out_dev)
+        prof = codec1.profile(False)
+        assert torch.equal(out_dev, x_dev)
+        del codec1, model1
     else:
         prof = codec.profile(False)
     barrier()
@@ -358,7 +366,7 @@ def main():
     fl, ab, sg = conv_flops(cfg), ans_bytes(cfg), sigmoids(cfg)
     FP64_PER_SIGMOID = 27        # FP64-pipe instructions per cdf value in k_rows' SASS (DESIGN.md "ANS kernels")
     fp64_peak = _lib.measure_fp64_peak()                                     # DFMA lanes/s, measured on this GPU
-    Bl = B // max(args.lanes, 1) if args.lanes > 1 else B        # images per kernel launch (per lane)
+    Bl = B                                                       # images per profiled kernel launch
     nsig_z, nsig_x = cfg.zdim * (cfg.zsupport - 1) * Bl, cfg.xdim * 255 * Bl
     # algorithmic work of ONE launch (B images, one direction).  Coder kernels: compulsory HBM bytes = mu,sigma
     # float32 + int16 symbol per symbol-op; they are FP64-pipe bound, so an fp64 fraction is added.
@@ -419,8 +427,9 @@ def main():
                     "d2h_bytes_per_step": int(bs_bytes + out_host.numel()), "ms_per_step": 1e3 * e2e_s / args.steps},
             "roofline": roofline, "kernels": kernels, "clocks": clocks,
             "kernels_timing": ("CUDA events around every launch inside the timed region" if args.lanes <= 1 else
-                               f"CUDA events around every launch in a serial replay of the same {args.steps} steps (lanes back to back on one "
-                               "stream, same kernels and launch shapes); the timed region itself runs the lanes concurrently")}
+                               f"CUDA events around every launch in a serial replay of the same {args.steps} steps by a single-lane codec at the "
+                               f"full batch of {B} (same kernels); the timed region itself runs {args.lanes} lanes of {B // args.lanes} concurrently, "
+                               "where per-kernel event times overlap and cannot be attributed")}
     if gather_ms is not None:
         line["bitstream_gather_ms"] = gather_ms
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
