@@ -1,0 +1,92 @@
+"""Variable-size images as chained 32x32 block streams + the reference's demo container format.
+
+Reference: block tiling `extract_blocks` / `unextract_blocks` (benchmark_compress.py:20-39), the demo codec
+(demo_compress.py:72-162 compress, :268-284 file format; demo_decompress.py:69-148, :216-227).  One image =
+ONE ANS chain over its blocks (imagenetcrop_compress.py:127-210); different images are independent chains, so
+a set of images is coded as a StreamSet with one stream per image: step t codes block t of every image that
+has more than t blocks (images are ordered by block count so the active streams are always a prefix).
+
+Container (np.uint32 array, what demo_compress.py saves with np.save):
+    [ words that were actually borrowed or produced ..., head_lo, head_hi, nblocks, h, w ]
+Blocks are fed CHW like the demo path does (demo_compress.py:120), not the HWC quirk of
+imagenetcrop_compress.py:130.
+"""
+import numpy as np
+import torch
+
+from .codec import BITSWAP
+from .streams import StreamSet
+from .synthetic import initial_words
+
+
+def extract_blocks(arr, block_size=(32, 32)):
+    """HWC uint8 image -> (blocks [n, 32, 32, C] row-major over the block grid, h, w) with h, w cropped down to
+    multiples of the block size (benchmark_compress.py:20-31)."""
+    bh, bw = block_size
+    h, w, c = arr.shape
+    h -= h % bh
+    w -= w % bw
+    arr = arr[:h, :w]
+    blocks = arr.reshape(h // bh, bh, w // bw, bw, c).swapaxes(1, 2).reshape(-1, bh, bw, c)
+    return blocks, h, w
+
+
+def unextract_blocks(blocks, h, w):
+    """Inverse of extract_blocks (benchmark_compress.py:35-39)."""
+    n, bh, bw, c = blocks.shape
+    return blocks.reshape(h // bh, w // bw, bh, bw, c).swapaxes(1, 2).reshape(h, w, c)
+
+
+def compress_images(codec, images, excess_state_len=10000, seed=100, scheme=BITSWAP):
+    """images: list of HWC uint8 arrays (any sizes >= 32x32).  Returns one container array per image.
+    Every chain starts from the reference's initial state: `excess_state_len` random words drawn with
+    np.random.seed(100) (demo_compress.py:113-115, :202)."""
+    tiled = [extract_blocks(np.asarray(im)) for im in images]
+    order = sorted(range(len(images)), key=lambda i: (-tiled[i][0].shape[0], i))
+    nblk = [tiled[i][0].shape[0] for i in order]
+    n = len(images)
+    ss = StreamSet(n, excess_state_len + 1400 * max(nblk) + 64)
+    w, head = initial_words(excess_state_len, seed=seed)
+    ss.fill(w, head)
+    for t in range(max(nblk)):
+        active = sum(1 for b in nblk if b > t)
+        x = np.stack([tiled[order[j]][0][t] for j in range(active)]).transpose(0, 3, 1, 2)     # -> CHW (demo_compress.py:120)
+        codec.encode(ss, torch.from_numpy(np.ascontiguousarray(x)).cuda(), first=0, scheme=scheme)
+    torch.cuda.synchronize()
+    ss.raise_on_error()
+    words, offs, heads, _ = ss.export()
+    lo = ss.min_words()                                       # never-borrowed initial words (demo_compress.py:137,160)
+    out = [None] * n
+    for j, i in enumerate(order):
+        ws = words[offs[j] + lo[j]:offs[j + 1]]
+        hd = int(heads[j])
+        _, h, wd = tiled[i]
+        tail = np.array([hd & 0xffffffff, hd >> 32, nblk[j], h, wd], dtype=np.uint32)           # demo_compress.py:272-279
+        out[i] = np.concatenate([ws.astype(np.uint32), tail])
+    return out
+
+
+def decompress_images(codec, containers, channels=3, scheme=BITSWAP):
+    """Inverse of compress_images: list of container arrays -> list of HWC uint8 images (cropped sizes)."""
+    meta = []
+    for c in containers:
+        c = np.asarray(c, dtype=np.uint32)
+        nblocks, h, w = int(c[-3]), int(c[-2]), int(c[-1])                                      # demo_decompress.py:216-219
+        head = (int(c[-4]) << 32) | int(c[-5])                                                  # :222
+        meta.append((c[:-5], head, nblocks, h, w))
+    order = sorted(range(len(containers)), key=lambda i: (-meta[i][2], i))
+    nblk = [meta[i][2] for i in order]
+    n = len(containers)
+    ss = StreamSet(n, max(len(meta[i][0]) for i in order) + 64)
+    ss.import_lists([[int(v) for v in meta[i][0]] + [meta[i][1]] for i in order])
+    blocks = [np.zeros((b, 32, 32, channels), dtype=np.uint8) for b in nblk]
+    for t in reversed(range(max(nblk))):
+        active = sum(1 for b in nblk if b > t)
+        x = codec.decode(ss, active, first=0, scheme=scheme).cpu().numpy().transpose(0, 2, 3, 1)
+        for j in range(active):
+            blocks[j][t] = x[j]
+    ss.raise_on_error()
+    out = [None] * n
+    for j, i in enumerate(order):
+        out[i] = unextract_blocks(blocks[j], meta[i][3], meta[i][4])
+    return out

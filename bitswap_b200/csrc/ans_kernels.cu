@@ -37,6 +37,8 @@ extern "C" int bsw_streams_create(bsw_streams **out, int n_streams, int64_t capa
     BSW_CUDA(cudaMalloc(&s->nwords, sizeof(int32_t) * s->B));
     BSW_CUDA(cudaMalloc(&s->heads, sizeof(uint64_t) * s->B));
     BSW_CUDA(cudaMalloc(&s->flags, sizeof(int32_t) * s->B));
+    BSW_CUDA(cudaMalloc(&s->minwords, sizeof(int32_t) * s->B));
+    BSW_CUDA(cudaMemset(s->minwords, 0, sizeof(int32_t) * s->B));
     BSW_CUDA(cudaMemset(s->nwords, 0, sizeof(int32_t) * s->B));
     BSW_CUDA(cudaMemset(s->heads, 0, sizeof(uint64_t) * s->B));
     BSW_CUDA(cudaMemset(s->flags, 0, sizeof(int32_t) * s->B));
@@ -45,7 +47,7 @@ extern "C" int bsw_streams_create(bsw_streams **out, int n_streams, int64_t capa
 }
 extern "C" int bsw_streams_destroy(bsw_streams *s) {
     if (!s) return BSW_OK;
-    cudaFree(s->words); cudaFree(s->nwords); cudaFree(s->heads); cudaFree(s->flags);
+    cudaFree(s->words); cudaFree(s->nwords); cudaFree(s->heads); cudaFree(s->flags); cudaFree(s->minwords);
     delete s;
     return BSW_OK;
 }
@@ -65,6 +67,7 @@ extern "C" int bsw_streams_import(bsw_streams *s, int first, int count, const ui
                                 sizeof(uint32_t) * len, cudaMemcpyHostToDevice));
     }
     BSW_CUDA(cudaMemcpy(s->nwords + first, n.data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice));
+    BSW_CUDA(cudaMemcpy(s->minwords + first, n.data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice));
     BSW_CUDA(cudaMemcpy(s->heads + first, heads_host, sizeof(uint64_t) * count, cudaMemcpyHostToDevice));
     BSW_CUDA(cudaMemset(s->flags + first, 0, sizeof(int32_t) * count));
     return BSW_OK;
@@ -74,7 +77,7 @@ __global__ void k_streams_fill(bsw_streams sv, const uint32_t *src, int64_t n, u
     int b = blockIdx.y;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         sv.words[(int64_t)b * sv.cap + i] = src[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sv.nwords[b] = (int32_t)n; sv.heads[b] = head; sv.flags[b] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sv.nwords[b] = (int32_t)n; sv.minwords[b] = (int32_t)n; sv.heads[b] = head; sv.flags[b] = 0; }
 }
 extern "C" int bsw_streams_fill(bsw_streams *s, const uint32_t *words_host, int64_t nwords, uint64_t head) {
     BSW_REQUIRE(s && nwords >= 0 && nwords <= s->cap, "bsw_streams_fill: nwords exceeds capacity");
@@ -99,6 +102,14 @@ extern "C" int bsw_streams_sizes(bsw_streams *s, int64_t *nwords_host, uint64_t 
     }
     if (heads_host) BSW_CUDA(cudaMemcpy(heads_host, s->heads, sizeof(uint64_t) * s->B, cudaMemcpyDeviceToHost));
     if (flags_host) BSW_CUDA(cudaMemcpy(flags_host, s->flags, sizeof(int32_t) * s->B, cudaMemcpyDeviceToHost));
+    return BSW_OK;
+}
+extern "C" int bsw_streams_min_words(bsw_streams *s, int64_t *min_host) {
+    BSW_REQUIRE(s && min_host, "null argument");
+    BSW_CUDA(cudaDeviceSynchronize());
+    std::vector<int32_t> n(s->B);
+    BSW_CUDA(cudaMemcpy(n.data(), s->minwords, sizeof(int32_t) * s->B, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < s->B; ++i) min_host[i] = n[i];
     return BSW_OK;
 }
 extern "C" int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t *words_host,
@@ -163,7 +174,7 @@ struct WarpStream {
         wbuf = 0;
     }
     __device__ __forceinline__ void close(const bsw_streams &sv, int b, int lane) {
-        if (lane == 0) { sv.heads[b] = x; sv.nwords[b] = len; sv.flags[b] = err; }
+        if (lane == 0) { sv.heads[b] = x; sv.nwords[b] = len; sv.flags[b] = err; if (len < sv.minwords[b]) sv.minwords[b] = len; }
     }
     // ---- pop side: window slides downward -------------------------------------------------------
     __device__ __forceinline__ uint32_t pop_word(int lane) {     // caller guarantees len > 0

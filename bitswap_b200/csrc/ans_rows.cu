@@ -31,7 +31,7 @@ struct WarpStream2 {          // same state handling as ans_kernels.cu's WarpStr
         err = sv.flags[b]; wbase = -1; wbuf = 0;
     }
     __device__ __forceinline__ void close(const bsw_streams &sv, int b, int lane) {
-        if (lane == 0) { sv.heads[b] = x; sv.nwords[b] = len; sv.flags[b] = err; }
+        if (lane == 0) { sv.heads[b] = x; sv.nwords[b] = len; sv.flags[b] = err; if (len < sv.minwords[b]) sv.minwords[b] = len; }
     }
     __device__ __forceinline__ uint32_t pop_word(int lane) {
         int idx = len - 1;

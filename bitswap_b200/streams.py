@@ -64,6 +64,12 @@ class StreamSet:
         check(lib().bsw_streams_sizes(self._h, n.ctypes.data, h.ctypes.data, f.ctypes.data))
         return n, h, f
 
+    def min_words(self):
+        """Lowest word count each stream reached since import/fill (reference: `excess_state_len - 1`)."""
+        n = np.zeros(self.n, dtype=np.int64)
+        check(lib().bsw_streams_min_words(self._h, n.ctypes.data))
+        return n
+
     def export(self, first=0, count=None):
         """Packed export: (words uint32[sum], offsets int64[count+1], heads uint64[count], flags)."""
         count = self.n - first if count is None else count

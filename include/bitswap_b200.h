@@ -67,6 +67,9 @@ int bsw_streams_import(bsw_streams *s, int first, int count, const uint32_t *wor
 int bsw_streams_fill(bsw_streams *s, const uint32_t *words_host, int64_t nwords, uint64_t head);
 /* Word counts (list length - 1), heads and per-stream status flags (bsw_status values). Synchronous. */
 int bsw_streams_sizes(bsw_streams *s, int64_t *nwords_host, uint64_t *heads_host, int32_t *flags_host);
+/* Lowest word count each stream has reached since import/fill: the part of the initial random words that was never
+ * borrowed and can be trimmed from a stored bitstream (demo_compress.py:137,160 `excess_state_len`). Synchronous. */
+int bsw_streams_min_words(bsw_streams *s, int64_t *min_host);
 /* Packed export: stream i's words go to words_host[offsets_host[i] ...). Synchronous. */
 int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t *words_host, const int64_t *offsets_host);
 /* Raw device views for device-resident pipelines (NCCL gathers, custom kernels). */

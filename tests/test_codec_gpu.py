@@ -386,3 +386,41 @@ def test_pipelined_codec_equals_single_codec():
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy(), imgs[xi])
     assert ss.export_lists() == states
+
+
+def test_container_variable_size_images_vs_oracle_demo_procedure():
+    """BASELINE config 5 shape: variable-size images, each ONE chain over its 32x32 blocks, many images at once.
+    The containers must equal what the reference's demo procedure (demo_compress.py:113-162,268-284) yields when the
+    oracle runs it per image with the same (GPU) nets, and decompress_images must restore the cropped images."""
+    from bitswap_b200.container import compress_images, decompress_images, extract_blocks
+    cfg = preset("tiny3")                 # RGB, conditional x-scale: the imagenetcrop model family
+    sizes = [(64, 96), (32, 32), (100, 70), (40, 129)]
+    rs = np.random.RandomState(5)
+    images = [rs.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in sizes]
+    cfg_, m, sd, zend, zcen, codec, _ = _setup("tiny3", len(images), 64)
+    conts = compress_images(codec, images, excess_state_len=3000)
+    # oracle: the reference demo loop, one image at a time
+    orc = O.BitSwapOracle(cfg, O.ModelOracle(cfg, sd), zend, zcen, coder="c", pmf="c")
+
+    def gpu_net(kind, level, given):
+        f = m.infer(level) if kind == "infer" else m.generate(level)
+        mu, sc = f(given.cuda())
+        return mu.cpu(), sc.cpu()
+    orc._net = gpu_net
+    for img, cont in zip(images, conts):
+        blocks, h, w = extract_blocks(img)
+        wds, head = synthetic.initial_words(3000, seed=100)
+        st = O.CState(wds, head)
+        low = st.n
+        # track the lowest stack depth like demo_compress.py:137 (after every pop)
+        pops = []
+        orc.trace = pops
+        for b in blocks:
+            st = orc.encode_image(st, b.transpose(2, 0, 1))
+        low = min([ln - 1 for tag, ln, _ in pops if tag.startswith("pop")] + [low])
+        want = np.concatenate([st.words[low:st.n], np.array([st.head & 0xffffffff, st.head >> 32, len(blocks), h, w], dtype=np.uint64)]).astype(np.uint32)
+        assert np.array_equal(cont, want)
+    back = decompress_images(codec, conts)
+    for img, rec in zip(images, back):
+        h, w = img.shape[0] - img.shape[0] % 32, img.shape[1] - img.shape[1] % 32
+        assert np.array_equal(rec, img[:h, :w])
