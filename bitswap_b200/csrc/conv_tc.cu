@@ -22,6 +22,7 @@
 //     in the batch (the decoder must regenerate the encoder's tables exactly).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <vector>
 #include "bsw_common.cuh"
 #include "nets.cuh"
@@ -80,6 +81,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -110,6 +119,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -135,9 +148,13 @@ struct TcArgs {
     int A_elu;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
-          const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
+// CLUSTER: the two N-half CTAs of an image form a 2-CTA cluster and share the activation tile: CTA 0 loads the hi
+// plane, CTA 1 the lo plane, each TMA multicast into both CTAs' shared memory (L2->SM traffic per CTA 48 -> 32 KB
+// per k-block).  A stage is free only when BOTH consumers released it, so the MMA commit arrives on both CTAs'
+// empty barriers.
+template <bool CLUSTER>
+__device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const CUtensorMap &amap_lo, const CUtensorMap &wmap_hi,
+                                             const CUtensorMap &wmap_lo, const TcArgs &a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = (uint64_t *)(smem + NSTAGE * STAGE_BYTES);
@@ -154,7 +171,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_lo) : "memory");
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER ? 2 : 1); }
         mbar_init(acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -163,9 +180,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CLUSTER) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const int crank = CLUSTER ? (int)blockIdx.y : 0;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -178,8 +196,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t *st = smem + stage * STAGE_BYTES;
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img);
-                tma_load_4d(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img);
+                if (CLUSTER) {
+                    if (crank == 0) tma_load_4d_mc(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img, 3);
+                    else tma_load_4d_mc(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img, 3);
+                } else {
+                    tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img);
+                    tma_load_4d(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img);
+                }
                 tma_load_3d(st + 2 * TILE_BYTES, &wmap_hi, &full_bar[stage], c0, co0, tap);
                 tma_load_3d(st + 2 * TILE_BYTES + WTILE_BYTES, &wmap_lo, &full_bar[stage], c0, co0, tap);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -208,7 +231,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
                         umma_bf16(d_cross, a_hi, b_lo, 1);
                     }
                 }
-                umma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+                if (CLUSTER) umma_commit_mc(&empty_bar[stage], 3);   // frees the stage in BOTH CTAs when these MMAs retire
+                else umma_commit(&empty_bar[stage]);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             umma_commit(acc_bar);                        // accumulators complete
@@ -268,12 +292,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ C
         }
         tc_fence_before();
     }
-    __syncthreads();
+    if (CLUSTER) cluster_sync_all(); else __syncthreads();     // (cluster: the peer may still signal my barriers until here)
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
+          const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
+    conv_tc_body<false>(amap_hi, amap_lo, wmap_hi, wmap_lo, a);
+}
+__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(TC_THREADS, 1)
+k_conv_tc_c2(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
+             const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
+    conv_tc_body<true>(amap_hi, amap_lo, wmap_hi, wmap_lo, a);
 }
 
 // float32 NHWC -> bf16 hi/lo planes (used once per net, after the SIMT in-conv)
@@ -368,6 +403,7 @@ int bsw_model_tc_prepare(bsw_model *m) {
     }
     m->tc_slots = slots;
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     m->tc_ready = true;
     return BSW_OK;
 }
@@ -410,8 +446,13 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
-    k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1], s.map_hi,
-                                                           s.map_lo, t);
+    static const bool use_cluster = !(getenv("BSW_TC_NO_CLUSTER") && getenv("BSW_TC_NO_CLUSTER")[0] == '1');
+    if (use_cluster)
+        k_conv_tc_c2<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
+                                                                              s.map_hi, s.map_lo, t);
+    else
+        k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
+                                                                           s.map_hi, s.map_lo, t);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
 }
