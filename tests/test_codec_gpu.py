@@ -424,3 +424,32 @@ def test_container_variable_size_images_vs_oracle_demo_procedure():
     for img, rec in zip(images, back):
         h, w = img.shape[0] - img.shape[0] % 32, img.shape[1] - img.shape[1] % 32
         assert np.array_equal(rec, img[:h, :w])
+
+
+def test_gpu_discretize_builds_usable_bins():
+    """discretize() with the reference's signature on the GPU nets: table layout, float32 top level, uniform
+    lower levels covering every sample -- and the codec round-trips with the tables it built."""
+    from bitswap_b200.discretization import discretize
+    cfg = preset("tiny3")
+    sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=True)
+    m = Model.from_config(cfg, max_batch=128).load_state_dict(sd)
+    m.compress()
+    imgs = torch.from_numpy(synthetic.synthetic_images(cfg, 512, seed=17, kind="smooth"))
+    zend, zcen = discretize(cfg.nz, cfg.quantbits, torch.float64, "cpu", m, "synthetic", images=imgs, ppb=8)
+    S = cfg.zsupport
+    assert zend.shape == (cfg.nz, cfg.zdim, S - 1) and zcen.shape == (cfg.nz, cfg.zdim, S) and zend.dtype == torch.float64
+    assert torch.all(zend[:, :, 1:] > zend[:, :, :-1])                                   # strictly increasing endpoints
+    ref_e, _ = synthetic.synthetic_bins(cfg, seed=0)
+    assert torch.equal(zend[-1], ref_e[-1])                                              # top level == rand.Bins (float32)
+    w = zend[0, :, 1:] - zend[0, :, :-1]
+    assert (w.max(dim=1).values - w.min(dim=1).values).max() < 1e-9                     # uniform width per dimension
+    B = 4
+    codec = BitSwapCodec(cfg, m, Bins(cfg, zend, zcen), B)
+    ss = StreamSet(B, 8192)
+    wds, head = synthetic.initial_words(3000, seed=100)
+    ss.fill(wds, head)
+    x = imgs[:B].cuda()
+    codec.encode(ss, x)
+    out = codec.decode(ss, B)
+    ss.raise_on_error()
+    assert torch.equal(out, x)
