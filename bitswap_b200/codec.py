@@ -78,6 +78,10 @@ class BitSwapCodec:
     CATEGORIES = ("misc", "conv_in", "conv_dense3x3", "conv_dense5x5", "conv_head", "pop_z", "push_z", "pop_x",
                   "push_x", "prior", "rows_z", "rows_x")
 
+    def set_dual_stream(self, on=True):
+        """True: convs on a high-priority internal stream, coder kernels on a low-priority one (default off)."""
+        check(lib().bsw_codec_set_dual_stream(self._h, int(on)))
+
     def set_two_phase(self, on=True):
         """True (default): parallel row-table kernel + serial coder; False: fused one-warp-per-stream kernels."""
         check(lib().bsw_codec_set_two_phase(self._h, int(on)))
@@ -149,6 +153,10 @@ class PipelinedCodec:
     def set_two_phase(self, on=True):
         for c in self.codecs:
             c.set_two_phase(on)
+
+    def set_dual_stream(self, on=True):
+        for c in self.codecs:
+            c.set_dual_stream(on)
 
     @property
     def last_launches(self):

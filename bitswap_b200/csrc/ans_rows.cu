@@ -76,13 +76,14 @@ __device__ __forceinline__ void warp_argmax(uint32_t &val, int &idx) {       // 
     }
 }
 
-constexpr int RW = 8;        // warps per CTA in phase A
+constexpr int RW = 16;       // warps per CTA in phase A: 512 threads x <=64 registers = half an SM's register file, so two
+                             // of these CTAs fill an SM, or one of them sits beside one k_conv_tc CTA (codec.cu overlap)
 
 // ---- phase A ----------------------------------------------------------------------------------------------------
 // Bin ownership is interleaved: lane owns bins k = r*32 + lane, r = 0..NB-1, so endpoint loads are coalesced
 // 256-byte lines and chunk r (32 consecutive bins) is exactly one warp-wide step.
 template <int NB, bool POP>
-__global__ void __launch_bounds__(RW * 32, 4) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
+__global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint2 *__restrict__ pairs, uint32_t *__restrict__ coarse,
         uint2 *__restrict__ fix) {

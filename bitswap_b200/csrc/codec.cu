@@ -23,6 +23,12 @@ struct bsw_codec {
     uint32_t *priorP, *priorC;          // Logistic(0,1) prior tables over zendpoints[-1], shared by all streams
     int64_t launches;
     BswProf prof;
+    // overlap: convs go to a high-priority internal stream, coder kernels to a low-priority one, chained by events, so
+    // that (with several codecs in flight) tensor-bound conv CTAs and FP64-bound coder CTAs share SMs
+    cudaStream_t st_hi = nullptr, st_lo = nullptr;
+    cudaEvent_t ev[8];
+    int ev_next = 0;
+    int dual_stream = 0;     // measured on B200: no gain (lanes=4: 350 ms/step without, 378 with) -- kept as an option
 };
 
 // internal int16-symbol variants of the table-driven coder (ans_kernels.cu)
@@ -79,6 +85,11 @@ extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int 
     cudaFree(dms);
     if (rc) return rc;
     c->launches = 0;
+    int lo_p = 0, hi_p = 0;
+    BSW_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));          // (numerically lower = higher priority)
+    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_hi, cudaStreamNonBlocking, hi_p));
+    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_lo, cudaStreamNonBlocking, lo_p));
+    for (auto &e : c->ev) BSW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = c;
     return BSW_OK;
 }
@@ -89,6 +100,9 @@ extern "C" int bsw_codec_destroy(bsw_codec *c) {
     cudaFree(c->sym[0]); cudaFree(c->sym[1]); cudaFree(c->xsym);
     for (auto p : c->zs) cudaFree(p);
     cudaFree(c->priorP); cudaFree(c->priorC); cudaFree(c->scratch);
+    if (c->st_hi) cudaStreamDestroy(c->st_hi);
+    if (c->st_lo) cudaStreamDestroy(c->st_lo);
+    for (auto &e : c->ev) cudaEventDestroy(e);
     delete c;
     return BSW_OK;
 }
@@ -96,6 +110,14 @@ extern "C" int64_t bsw_codec_last_launches(const bsw_codec *c) { return c ? c->l
 
 // Per-category kernel timing for bench.py's roofline (CUDA events on the launching stream).
 /* 1 (default): two-phase coder (parallel row tables + serial coder); 0: fused one-warp-per-stream kernels. */
+/* 1: convs on a high-priority internal stream, coder kernels on a low-priority one (event-chained);
+ * 0 (default): everything on the caller's stream. */
+extern "C" int bsw_codec_set_dual_stream(bsw_codec *c, int on) {
+    BSW_REQUIRE(c, "null codec");
+    c->dual_stream = on ? 1 : 0;
+    return BSW_OK;
+}
+
 extern "C" int bsw_codec_set_two_phase(bsw_codec *c, int on) {
     BSW_REQUIRE(c, "null codec");
     c->two_phase = on ? 1 : 0;
@@ -115,12 +137,27 @@ extern "C" int bsw_codec_profile(bsw_codec *c, int enable, double *ms_out, int64
 
 namespace {
 struct Ctx {
-    bsw_codec *c; bsw_streams *s; int first, count; cudaStream_t st;
+    bsw_codec *c; bsw_streams *s; int first, count; cudaStream_t st;      // st = stream the next kernel goes to
     int nl = 0;
+    cudaStream_t caller = nullptr;
+    // move the chain to `target`: everything enqueued so far (on st) happens-before what follows on target
+    void use(cudaStream_t target) {
+        if (target == st) return;
+        cudaEvent_t e = c->ev[c->ev_next];
+        c->ev_next = (c->ev_next + 1) & 7;
+        cudaEventRecord(e, st);
+        cudaStreamWaitEvent(target, e, 0);
+        st = target;
+    }
+    void begin(cudaStream_t user) { caller = user; st = user; if (c->dual_stream) use(c->st_lo); }
+    void end() { use(caller); }
+    void conv_stream() { if (c->dual_stream) use(c->st_hi); }
+    void coder_stream() { if (c->dual_stream) use(c->st_lo); }
     const double *zend(int lvl) const { return c->b->zend + (size_t)lvl * c->zdim * c->S; }
-    int infer(int zi) { return bsw_model_run(c->m, true, zi, c->given, count, c->mu, c->scale, 1, st, &nl, &c->prof); }
-    int generate(int zi) { return bsw_model_run(c->m, false, zi, c->given, count, c->mu, c->scale, 0, st, &nl, &c->prof); }
+    int infer(int zi) { conv_stream(); return bsw_model_run(c->m, true, zi, c->given, count, c->mu, c->scale, 1, st, &nl, &c->prof); }
+    int generate(int zi) { conv_stream(); return bsw_model_run(c->m, false, zi, c->given, count, c->mu, c->scale, 0, st, &nl, &c->prof); }
     int gather_x(const uint8_t *x) {
+        coder_stream();
         ++nl;
         c->prof.begin(CAT_MISC, st);
         int rc = bsw_gather_xcentres(x, c->given, (int64_t)count * c->xdim, st);
@@ -129,6 +166,7 @@ struct Ctx {
     }
     int gather_x16(const int16_t *x);
     int gather_z(int lvl, const int16_t *sym) {
+        coder_stream();
         ++nl;
         c->prof.begin(CAT_MISC, st);
         int rc = bsw_gather_zcentres(c->b, lvl, sym, c->given, count, st);
@@ -137,6 +175,7 @@ struct Ctx {
     }
     // q(z_{zi+1} | .) / p(z_zi | .) tables over level `lvl` endpoints
     int pop_z(int lvl, int16_t *sym) {
+        coder_stream();
         if (!c->two_phase) {
             ++nl;
             c->prof.begin(CAT_POP_Z, st);
@@ -155,6 +194,7 @@ struct Ctx {
         return rc;
     }
     int push_z(int lvl, const int16_t *sym) {
+        coder_stream();
         if (!c->two_phase) {
             ++nl;
             c->prof.begin(CAT_PUSH_Z, st);
@@ -175,6 +215,7 @@ struct Ctx {
     // p(x | z_1): ImageBins endpoints (one shared row), 8-bit quantisation (cifar_compress.py:202)
     int64_t xss() const { return c->m->d.cond_xscale ? c->xdim : 0; }
     int pop_x(int16_t *sym) {
+        coder_stream();
         if (!c->two_phase) {
             ++nl;
             c->prof.begin(CAT_POP_X, st);
@@ -193,6 +234,7 @@ struct Ctx {
         return rc;
     }
     int push_x(const int16_t *sym) {
+        coder_stream();
         if (!c->two_phase) {
             ++nl;
             c->prof.begin(CAT_PUSH_X, st);
@@ -211,6 +253,7 @@ struct Ctx {
         return rc;
     }
     int push_prior(const int16_t *sym) {
+        coder_stream();
         ++nl;
         c->prof.begin(CAT_PRIOR, st);
         int rc = bsw_ans_push_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
@@ -218,6 +261,7 @@ struct Ctx {
         return rc;
     }
     int pop_prior(int16_t *sym) {
+        coder_stream();
         ++nl;
         c->prof.begin(CAT_PRIOR, st);
         int rc = bsw_ans_pop_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
@@ -230,6 +274,7 @@ __global__ void k_gather_x16(const int16_t *__restrict__ x, float *__restrict__ 
     if (i < n) out[i] = (float)(((double)x[i] - 127.5) / 127.5);
 }
 int Ctx::gather_x16(const int16_t *x) {
+    coder_stream();
     ++nl;
     int64_t n = (int64_t)count * c->xdim;
     k_gather_x16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, c->given, n);
@@ -253,6 +298,7 @@ static int ensure_zs(bsw_codec *c) {
 extern "C" int bsw_codec_encode(bsw_codec *c, bsw_streams *s, int first, int count, const uint8_t *x, int scheme, void *stream) {
     RC(codec_args_ok(c, s, first, count, x));
     Ctx k{c, s, first, count, (cudaStream_t)stream};
+    k.begin((cudaStream_t)stream);
     const int nz = c->nz;
     int64_t nx = (int64_t)count * c->xdim;
     k_u8_to_i16<<<(unsigned)((nx + 255) / 256), 256, 0, k.st>>>(x, c->xsym, nx);
@@ -286,6 +332,7 @@ extern "C" int bsw_codec_encode(bsw_codec *c, bsw_streams *s, int first, int cou
         zsym = c->zs[nz - 1];
     }
     RC(k.push_prior(zsym));                                                                 // :245-250
+    k.end();
     c->launches = k.nl;
     return BSW_OK;
 }
@@ -293,6 +340,7 @@ extern "C" int bsw_codec_encode(bsw_codec *c, bsw_streams *s, int first, int cou
 extern "C" int bsw_codec_decode(bsw_codec *c, bsw_streams *s, int first, int count, uint8_t *x, int scheme, void *stream) {
     RC(codec_args_ok(c, s, first, count, x));
     Ctx k{c, s, first, count, (cudaStream_t)stream};
+    k.begin((cudaStream_t)stream);
     const int nz = c->nz;
     int16_t *ztop = c->sym[0], *sym = c->sym[1];
     if (scheme == 0) {
@@ -323,8 +371,10 @@ extern "C" int bsw_codec_decode(bsw_codec *c, bsw_streams *s, int first, int cou
         }
     }
     int64_t nx = (int64_t)count * c->xdim;
+    k.coder_stream();
     k_i16_to_u8<<<(unsigned)((nx + 255) / 256), 256, 0, k.st>>>(c->xsym, x, nx);
     BSW_LAUNCH_CHECK();
+    k.end();
     c->launches = k.nl + 1;
     return BSW_OK;
 }

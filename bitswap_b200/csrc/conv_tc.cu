@@ -300,7 +300,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// min-blocks 2 only caps the register count (<= 96/thread, 30.7K per CTA) so that one coder CTA (k_rows, 32.8K
+// registers) can share the SM with a conv CTA; shared memory still limits the kernel itself to one CTA per SM.
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
           const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
     conv_tc_body<false>(amap_hi, amap_lo, wmap_hi, wmap_lo, a);

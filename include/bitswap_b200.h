@@ -220,6 +220,10 @@ int bsw_codec_decode(bsw_codec *c, bsw_streams *s, int first, int count, uint8_t
                      void *stream);
 /* Number of kernel launches the last encode/decode call enqueued (bench.py's gpu_launches). */
 int64_t bsw_codec_last_launches(const bsw_codec *c);
+/* Stream placement inside one encode/decode call: 0 (default) = every kernel on the caller's stream; 1 = conv kernels
+ * on a high-priority internal stream, coder kernels on a low-priority one, chained with events and joined back into
+ * `stream` at the end (an experiment in co-scheduling tensor-bound and FP64-bound CTAs; measured no gain on B200). */
+int bsw_codec_set_dual_stream(bsw_codec *c, int on);
 /* Coder variant: 1 (default) = two-phase (ans_rows.cu: fully parallel float64 row tables, then the serial integer
  * coder), 0 = fused one-warp-per-stream kernels (bsw_logistic_push/pop).  Bit-identical results. */
 int bsw_codec_set_two_phase(bsw_codec *c, int on);
