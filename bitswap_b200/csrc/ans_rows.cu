@@ -195,21 +195,36 @@ __global__ void __launch_bounds__(BW * 32) k_pop_coarse(bsw_streams sv, int firs
     float mu_w = 0.f, sc_w = 1.f;
     uint2 fx_w = make_uint2(0, 0);
     int my_sym = 0;
-    // coarse cdf of the next row, prefetched (independent of the head)
-    uint32_t base_n = (lane < NB) ? __ldg(cb + (L - 1) * NB + lane) : 0xffffffffu;
+    // per-row scalars (mu, sigma, argmax, remnant) of a block of 32 rows, loaded one block ahead of their use
+    float mu_nx, sc_nx;
+    uint2 fx_nx;
+    {
+        int64_t r = ((L - 1) & ~(int64_t)31) + lane;
+        mu_nx = r < L ? mub[r] : 0.f;
+        sc_nx = r < L ? scb[r] : 1.f;
+        fx_nx = r < L ? __ldg(fb + r) : make_uint2(0, 0);
+    }
+    // coarse cdf rows are independent of the head: keep the loads two rows ahead of their use.  (They are issued AFTER
+    // the per-row shuffles below: the first version issued the load first and ncu showed every row stalling ~700 cycles
+    // on that load's scoreboard at the first shuffle, profiles/r1_ncu_popcoarse.md.)
+    uint32_t base_n1 = (lane < NB) ? __ldg(cb + (L - 1) * NB + lane) : 0xffffffffu;
+    uint32_t base_n2 = (lane < NB && L > 1) ? __ldg(cb + (L - 2) * NB + lane) : 0xffffffffu;
     for (int64_t i = L - 1; i >= 0; --i) {
         const int j32 = (int)(i & 31);
-        if (j32 == 31 || i == L - 1) {
-            int64_t r = (i & ~(int64_t)31) + lane;
-            mu_w = r < L ? mub[r] : 0.f;
-            sc_w = r < L ? scb[r] : 1.f;
-            fx_w = r < L ? __ldg(fb + r) : make_uint2(0, 0);
-        }
-        const uint32_t base = base_n;
-        if (i > 0) base_n = (lane < NB) ? __ldg(cb + (i - 1) * NB + lane) : 0xffffffffu;
+        const bool new_block = (j32 == 31 || i == L - 1);
+        if (new_block) { mu_w = mu_nx; sc_w = sc_nx; fx_w = fx_nx; }
         const double m_ = (double)__shfl_sync(FULL, mu_w, j32), s_ = (double)__shfl_sync(FULL, sc_w, j32);
         const int bi = (int)__shfl_sync(FULL, fx_w.x, j32);
         const uint32_t rem = __shfl_sync(FULL, fx_w.y, j32);
+        if (new_block) {                                  // the block below this one
+            int64_t r = (i & ~(int64_t)31) - 32 + lane;
+            mu_nx = r >= 0 ? mub[r] : 0.f;
+            sc_nx = r >= 0 ? scb[r] : 1.f;
+            fx_nx = r >= 0 ? __ldg(fb + r) : make_uint2(0, 0);
+        }
+        const uint32_t base = base_n1;
+        base_n1 = base_n2;
+        if (i > 1) base_n2 = (lane < NB) ? __ldg(cb + (i - 2) * NB + lane) : 0xffffffffu;
         const double rs = __ddiv_rn(1.0, s_);
         const uint32_t mm = (uint32_t)ws.x & mask;                                       // cifar_compress.py:60
         const int chunk = 31 - __clz(__ballot_sync(FULL, base <= mm));                   // base of lanes >= NB is UINT_MAX
