@@ -103,26 +103,42 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     BswExpRegs K;
     K.load();
     double saved = 0.0;                                   // cdf of lane 31 in the previous chunk (0 before bin 0)
-#pragma unroll 4
-    for (int r = 0; r < NB; ++r) {
-        const int k = r * 32 + lane;
-        // the row's last entry is the +1e300 pad: t clamps to +690 and the cdf comes out as exactly 1.0, which is
-        // the reference's `1. - cdfs[:,-1]` upper bound of the last bin (cifar_compress.py:184)
-        double c = bsw_cdf_fast_regs(__ldg(e + k), m, s, rs, K);
-        double rot = __shfl_sync(FULL, c, (lane + 31) & 31);
-        double prev = lane == 0 ? saved : rot;
-        saved = rot;
-        uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;      // :29 trunc, :32 +1
-        if (v > best) { best = v; bi = k; }
-        if (POP) {
-            uint32_t T = __reduce_add_sync(FULL, v);      // total of chunk r
-            if (lane == r) myT = T;
-            total += T;
-        } else {
-            total += v;
-            below += (k < sy) ? v : 0u;
-            if (k == sy) ps = v;
+    // endpoints are fetched one batch of UB chunks ahead of the arithmetic (software pipelining: ncu showed the first
+    // FP64 instruction of each value waiting on its load)
+    constexpr int UB = NB < 4 ? NB : 4;
+    double e_cur[UB], e_nxt[UB];
+#pragma unroll
+    for (int j = 0; j < UB; ++j) e_cur[j] = __ldg(e + j * 32 + lane);
+#pragma unroll 1
+    for (int rb = 0; rb < NB; rb += UB) {
+        if (rb + UB < NB) {
+#pragma unroll
+            for (int j = 0; j < UB; ++j) e_nxt[j] = __ldg(e + (rb + UB + j) * 32 + lane);
         }
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+            const int r = rb + j;
+            const int k = r * 32 + lane;
+            // the row's last entry is the +1e300 pad: t clamps to +690 and the cdf comes out as exactly 1.0, which is
+            // the reference's `1. - cdfs[:,-1]` upper bound of the last bin (cifar_compress.py:184)
+            double c = bsw_cdf_fast_regs(e_cur[j], m, s, rs, K);
+            double rot = __shfl_sync(FULL, c, (lane + 31) & 31);
+            double prev = lane == 0 ? saved : rot;
+            saved = rot;
+            uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;      // :29 trunc, :32 +1
+            if (v > best) { best = v; bi = k; }
+            if (POP) {
+                uint32_t T = __reduce_add_sync(FULL, v);      // total of chunk r
+                if (lane == r) myT = T;
+                total += T;
+            } else {
+                total += v;
+                below += (k < sy) ? v : 0u;
+                if (k == sy) ps = v;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UB; ++j) e_cur[j] = e_nxt[j];
     }
     warp_argmax(best, bi);
     const int64_t out = (int64_t)si * L + row;
