@@ -80,84 +80,88 @@ constexpr int RW = 16;       // warps per CTA in phase A: 512 threads x <=64 reg
                              // of these CTAs fill an SM, or one of them sits beside one k_conv_tc CTA (codec.cu overlap)
 
 // ---- phase A ----------------------------------------------------------------------------------------------------
-// Bin ownership is interleaved: lane owns bins k = r*32 + lane, r = 0..NB-1, so endpoint loads are coalesced
-// 256-byte lines and chunk r (32 consecutive bins) is exactly one warp-wide step.
+// One CTA = one row index for RW (=16) streams, one warp per stream.  The row's endpoints (shared by every stream) are
+// staged once per CTA into a padded shared-memory tile; lane l then owns the NB consecutive bins [l*NB, l*NB+NB), so the
+// cdf of the previous bin is already in a register (one shuffle per row instead of two per bin) and the 32-bin chunk
+// totals the pop side needs are lane-local sums (no per-chunk warp reduction).  ~42 issued instructions per cdf value,
+// 27 of them on the FP64 pipe.
+template <int NB>
+__device__ __forceinline__ int tile_idx2(int k) { return k + k / NB; }       // conflict-free for lane-blocked 8-byte reads
+
 template <int NB, bool POP>
 __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint2 *__restrict__ pairs, uint32_t *__restrict__ coarse,
         uint2 *__restrict__ fix) {
+    constexpr int S = 32 * NB;
+    __shared__ double tile[S + 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = blockIdx.x;                      // row index i within the level
     const int si = blockIdx.y * RW + warp;               // stream
+    {
+        const double *e = endp + row * ers;
+        for (int k = threadIdx.x; k < S; k += RW * 32) tile[tile_idx2<NB>(k)] = __ldg(e + k);
+    }
+    __syncthreads();
     if (si >= count) return;
     const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];
     const double rs = __ddiv_rn(1.0, s);
     const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));
-    const double *e = endp + row * ers;
     int sy = 0;
     if (!POP) sy = (int)sym[(int64_t)si * L + row];
+    const int owner = sy / NB, js = sy - owner * NB;     // push: lane and in-lane position of the coded symbol
 
-    uint32_t best = 0, total = 0, below = 0, ps = 0, myT = 0;
-    int bi = 0;
     BswExpRegs K;
     K.load();
-    double saved = 0.0;                                   // cdf of lane 31 in the previous chunk (0 before bin 0)
-    // endpoints are fetched one batch of UB chunks ahead of the arithmetic (software pipelining: ncu showed the first
-    // FP64 instruction of each value waiting on its load)
-    constexpr int UB = NB < 4 ? NB : 4;
-    double e_cur[UB], e_nxt[UB];
-#pragma unroll
-    for (int j = 0; j < UB; ++j) e_cur[j] = __ldg(e + j * 32 + lane);
-#pragma unroll 1
-    for (int rb = 0; rb < NB; rb += UB) {
-        if (rb + UB < NB) {
-#pragma unroll
-            for (int j = 0; j < UB; ++j) e_nxt[j] = __ldg(e + (rb + UB + j) * 32 + lane);
+    const double *my = tile + lane * (NB + 1);
+    // cdf at my last endpoint first: the next lane needs it as the lower neighbour of its first bin.  The row's very
+    // last entry is the +1e300 pad: t clamps to +690 and the cdf comes out as exactly 1.0, the reference's
+    // `1. - cdfs[:,-1]` upper bound of the last bin (cifar_compress.py:184).
+    const double c_last = bsw_cdf_fast_regs(my[NB - 1], m, s, rs, K);
+    const double up = __shfl_up_sync(FULL, c_last, 1);
+    double prev = lane == 0 ? 0.0 : up;
+    uint32_t lsum = 0, lbest = 0, pre = 0, pv = 0;
+    int lbi = 0;
+#pragma unroll 4
+    for (int j = 0; j < NB - 1; ++j) {
+        const double c = bsw_cdf_fast_regs(my[j], m, s, rs, K);
+        const uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;      // :29 trunc, :32 +1
+        prev = c;
+        lsum += v;
+        if (v > lbest) { lbest = v; lbi = j; }
+        if (!POP) {
+            pre += (j < js) ? v : 0u;
+            if (j == js) pv = v;
         }
-#pragma unroll
-        for (int j = 0; j < UB; ++j) {
-            const int r = rb + j;
-            const int k = r * 32 + lane;
-            // the row's last entry is the +1e300 pad: t clamps to +690 and the cdf comes out as exactly 1.0, which is
-            // the reference's `1. - cdfs[:,-1]` upper bound of the last bin (cifar_compress.py:184)
-            double c = bsw_cdf_fast_regs(e_cur[j], m, s, rs, K);
-            double rot = __shfl_sync(FULL, c, (lane + 31) & 31);
-            double prev = lane == 0 ? saved : rot;
-            saved = rot;
-            uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;      // :29 trunc, :32 +1
-            if (v > best) { best = v; bi = k; }
-            if (POP) {
-                uint32_t T = __reduce_add_sync(FULL, v);      // total of chunk r
-                if (lane == r) myT = T;
-                total += T;
-            } else {
-                total += v;
-                below += (k < sy) ? v : 0u;
-                if (k == sy) ps = v;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < UB; ++j) e_cur[j] = e_nxt[j];
     }
-    warp_argmax(best, bi);
+    {
+        const uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c_last, prev), mult)) + 1u;
+        lsum += v;
+        if (v > lbest) { lbest = v; lbi = NB - 1; }
+        if (!POP) {
+            pre += (NB - 1 < js) ? v : 0u;
+            if (NB - 1 == js) pv = v;
+        }
+    }
+    uint32_t incl = lsum;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    int bi = lane * NB + lbi;
+    warp_argmax(lbest, bi);                               // :35 first maximum of the row
+    const uint32_t rem = (1u << bits) - total;
     const int64_t out = (int64_t)si * L + row;
     if (POP) {
-        const uint32_t rem = (1u << bits) - total;        // :35
-        uint32_t incl = myT;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        uint32_t base = incl - myT + ((lane * 32 > bi) ? rem : 0u);
-        if (lane < NB) coarse[out * NB + lane] = base;
+        constexpr int LPC = 32 / NB;                      // lanes per 32-bin chunk
+        const uint32_t base = incl - lsum + ((lane * NB > bi) ? rem : 0u);
+        if (lane % LPC == 0) coarse[out * NB + lane / LPC] = base;
         if (lane == 0) fix[out] = make_uint2((uint32_t)bi, rem);
     } else {
-        total = __reduce_add_sync(FULL, total);
-        below = __reduce_add_sync(FULL, below);
-        ps = __shfl_sync(FULL, ps, sy & 31);
-        const uint32_t rem = (1u << bits) - total;
-        if (lane == 0) pairs[out] = make_uint2(ps + (bi == sy ? rem : 0u), below + (bi < sy ? rem : 0u));
+        const uint32_t cb = __shfl_sync(FULL, incl - lsum + pre, owner);      // integer cdf at the symbol, before the remnant
+        const uint32_t pb = __shfl_sync(FULL, pv, owner);
+        if (lane == 0) pairs[out] = make_uint2(pb + (bi == sy ? rem : 0u), cb + (bi < sy ? rem : 0u));
     }
 }
 
