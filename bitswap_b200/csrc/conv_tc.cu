@@ -44,6 +44,9 @@ struct TcState {
     // bf16 hi/lo activation planes, ping-pong: [max_batch, 256 px, 256 ch]
     __nv_bfloat16 *act[2][2];
     CUtensorMap act_map[2][2];
+    // in-conv input: the flat `given` re-laid as NHWC bf16 hi/lo planes with the (1..12) input channels padded to 32
+    __nv_bfloat16 *inp[2];
+    CUtensorMap inp_map[2];
     std::vector<void *> wbufs;
 };
 
@@ -140,6 +143,7 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x);
 
 struct TcArgs {
     int taps, ks;
+    int cchunks;             // 32-channel chunks per tap: 8 for the dense W->W convs, 1 for the in-convs
     const float *bias;       // [256]
     const float *resid;      // [n,256,256] fp32 or null
     float *T;                // trunk out or null
@@ -164,7 +168,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int img = blockIdx.x, co0 = blockIdx.y * BN;
-    const int nkb = a.taps * (256 / BK);
+    const int nkb = a.taps * a.cchunks;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_hi) : "memory");
@@ -191,7 +195,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
             const int r = a.ks / 2;
             int stage = 0, phase = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                int tap = kb >> 3, c0 = (kb & 7) * BK;
+                int tap = kb / a.cchunks, c0 = (kb - tap * a.cchunks) * BK;
                 int dy = tap / a.ks, dx = tap - dy * a.ks;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t *st = smem + stage * STAGE_BYTES;
@@ -329,6 +333,27 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// flat CHW `given` (float32) -> NHWC bf16 hi/lo planes with 32 channels (zero padded).  mode IN_CHW_Z: channel c at
+// given[c*256 + p]; IN_CHW_X: Squeeze2d(2) on the fly, channel c*4+fh*2+fw <- pixel (2h+fh, 2w+fw) of image channel c
+// (utils/torch/modules.py:183-185).
+__global__ void k_given_to_planes(const float *__restrict__ given, int in_dim, int cin, int mode, __nv_bfloat16 *__restrict__ hi,
+                                  __nv_bfloat16 *__restrict__ lo, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (image, pixel, channel)
+    if (i >= n * 256 * 32) return;
+    int ch = (int)(i & 31);
+    int p = (int)((i >> 5) & 255);
+    int64_t img = i >> 13;
+    float x = 0.f;
+    if (ch < cin) {
+        const float *src = given + img * in_dim;
+        int y = p >> 4, xx = p & 15;
+        x = (mode == IN_CHW_Z) ? src[ch * 256 + p] : src[(ch >> 2) * 1024 + (2 * y + ((ch >> 1) & 1)) * 32 + 2 * xx + (ch & 1)];
+    }
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
 int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
                const cuuint32_t *box) {
     static EncodeTiledFn fn = nullptr;
@@ -371,20 +396,34 @@ int bsw_model_tc_prepare(bsw_model *m) {
             cuuint32_t box[4] = {BK, 16, 16, 1};
             if (int rc = encode_map(&ts->act_map[b][pl], ts->act[b][pl], 4, dims, str, box)) return rc;
         }
-    // weights: [tap][o=256][c=256] bf16 hi/lo planes, K (=c) innermost
+    for (int pl = 0; pl < 2; ++pl) {
+        size_t elems = (size_t)m->d.max_batch * 256 * 32;
+        BSW_CUDA(cudaMalloc(&ts->inp[pl], elems * sizeof(__nv_bfloat16)));
+        cuuint64_t dims[4] = {32, 16, 16, (cuuint64_t)m->d.max_batch};
+        cuuint64_t str[3] = {32 * 2, 16 * 32 * 2, 256 * 32 * 2};
+        cuuint32_t box[4] = {BK, 16, 16, 1};
+        if (int rc = encode_map(&ts->inp_map[pl], ts->inp[pl], 4, dims, str, box)) return rc;
+    }
+    // weights: [tap][o=256][c=Kc] bf16 hi/lo planes, K (=c) innermost; Kc = 256 for the dense convs, 32 for the in-convs
     std::vector<TcSlot> *slots = new std::vector<TcSlot>();
-    for (auto &c : m->convs) {
+    std::vector<char> is_in(m->convs.size(), 0);
+    for (auto &np : m->infer) is_in[np.in_conv] = 1;
+    for (auto &np : m->gen) is_in[np.in_conv] = 1;
+    for (size_t ci_ = 0; ci_ < m->convs.size(); ++ci_) {
+        ConvSlot &c = m->convs[ci_];
         bool dense = (c.Cin == m->d.reswidth && c.Cout == m->d.reswidth);
-        if (!dense) continue;
+        bool inconv = is_in[ci_] && c.Cin <= 32 && c.Cout == m->d.reswidth;
+        if (!dense && !inconv) continue;
         BSW_REQUIRE(!c.host_w.empty(), "tc_prepare: host weights already released");
         const int taps = c.ks * c.ks;
-        std::vector<__nv_bfloat16> hi((size_t)taps * 256 * 256), lo(hi.size());
+        const int Kc = dense ? 256 : 32;
+        std::vector<__nv_bfloat16> hi((size_t)taps * 256 * Kc), lo(hi.size());
         for (int tp = 0; tp < taps; ++tp)
-            for (int ci = 0; ci < 256; ++ci)
+            for (int ci = 0; ci < Kc; ++ci)
                 for (int o = 0; o < 256; ++o) {
-                    float w = c.host_w[((size_t)tp * c.CinP + ci) * c.CoutP + o];
+                    float w = ci < c.CinP ? c.host_w[((size_t)tp * c.CinP + ci) * c.CoutP + o] : 0.f;
                     __nv_bfloat16 h = __float2bfloat16_rn(w);
-                    size_t idx = ((size_t)tp * 256 + o) * 256 + ci;
+                    size_t idx = ((size_t)tp * 256 + o) * Kc + ci;
                     hi[idx] = h;
                     lo[idx] = __float2bfloat16_rn(w - __bfloat162float(h));
                 }
@@ -395,8 +434,8 @@ int bsw_model_tc_prepare(bsw_model *m) {
         ts->wbufs.push_back(c.w_hi);
         ts->wbufs.push_back(c.w_lo);
         TcSlot s;
-        cuuint64_t dims[3] = {256, 256, (cuuint64_t)taps};
-        cuuint64_t str[2] = {256 * 2, 256 * 256 * 2};
+        cuuint64_t dims[3] = {(cuuint64_t)Kc, 256, (cuuint64_t)taps};
+        cuuint64_t str[2] = {(cuuint64_t)Kc * 2, (cuuint64_t)256 * Kc * 2};
         cuuint32_t box[3] = {BK, BN, 1};
         if (int rc = encode_map(&s.map_hi, c.w_hi, 3, dims, str, box)) return rc;
         if (int rc = encode_map(&s.map_lo, c.w_lo, 3, dims, str, box)) return rc;
@@ -415,6 +454,7 @@ void bsw_model_tc_release(bsw_model *m) {
     if (!ts) return;
     for (int b = 0; b < 2; ++b)
         for (int pl = 0; pl < 2; ++pl) cudaFree(ts->act[b][pl]);
+    for (int pl = 0; pl < 2; ++pl) cudaFree(ts->inp[pl]);
     for (void *p : ts->wbufs) cudaFree(p);
     delete ts;
     delete (std::vector<TcSlot> *)m->tc_slots;
@@ -444,6 +484,7 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     const TcSlot &s = (*(std::vector<TcSlot> *)m->tc_slots)[c.tc_index];
     TcArgs t;
     t.taps = c.ks * c.ks; t.ks = c.ks;
+    t.cchunks = 8;
     t.bias = c.bias; t.resid = a.resid; t.T = a.T; t.T_elu = a.T_elu;
     t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
@@ -459,5 +500,27 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
         k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
                                                                            s.map_hi, s.map_lo, t);
     BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+
+// In-conv on the tensor cores: `given` (flat CHW float32) -> 32-channel bf16 planes -> k_conv_tc with one channel chunk
+// per tap.  Epilogue as for every conv: T = ELU(raw) (the trunk), A planes = ELU(T) for the first ResNet layer.
+int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st, int *launches) {
+    TcState *ts = (TcState *)m->tc_state;
+    BSW_REQUIRE(ts && c.tc_index >= 0, "bsw_conv_tc_in: conv has no tensor-core weights");
+    const TcSlot &s = (*(std::vector<TcSlot> *)m->tc_slots)[c.tc_index];
+    int64_t cnt = n * 256 * 32;
+    k_given_to_planes<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(a.in, a.in_dim, c.Cin, a.in_mode, ts->inp[0], ts->inp[1], n);
+    BSW_LAUNCH_CHECK();
+    TcArgs t;
+    t.taps = c.ks * c.ks; t.ks = c.ks;
+    t.cchunks = 1;
+    t.bias = c.bias; t.resid = nullptr; t.T = a.T; t.T_elu = a.T_elu;
+    t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
+    t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
+    t.A_elu = a.A_elu;
+    k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
+    BSW_LAUNCH_CHECK();
+    *launches += 2;
     return BSW_OK;
 }

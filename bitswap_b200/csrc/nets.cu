@@ -444,13 +444,19 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
         a.w = c.w; a.bias = c.bias; a.CoutP = c.CoutP;
         a.out_mode = OUT_NHWC; a.T = T; a.T_elu = 1; a.A = has_blocks ? A : nullptr; a.A_elu = 1;
         prof->begin(CAT_CONV_IN, st);
-        if (int rc = bsw_conv_simt(a, c.ks, n, st)) return rc;
-        if (use_tc && has_blocks) {          // conv-input planes for the tensor-core layers: A -> bf16 hi/lo
-            if (int rc = bsw_tc_split(m, A, 0, n, st)) return rc;
+        if (use_tc && has_blocks && c.tc_index >= 0) {
+            // tensor-core in-conv: the trunk in float32, the first layer's input straight into the bf16 planes
+            a.A = nullptr; a.A_planes = 0;
+            if (int rc = bsw_conv_tc_in(m, c, a, n, st, launches)) return rc;
+        } else {
+            if (int rc = bsw_conv_simt(a, c.ks, n, st)) return rc;
             ++*launches;
+            if (use_tc && has_blocks) {          // conv-input planes for the tensor-core layers: A -> bf16 hi/lo
+                if (int rc = bsw_tc_split(m, A, 0, n, st)) return rc;
+                ++*launches;
+            }
         }
         prof->end(st);
-        ++*launches;
     }
     for (size_t bi = 0; bi < np.blocks.size(); ++bi) {
         const BlockPlan &bp = np.blocks[bi];

@@ -105,3 +105,4 @@ int bsw_model_tc_prepare(bsw_model *m);
 void bsw_model_tc_release(bsw_model *m);
 int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st);
 int bsw_tc_split(bsw_model *m, const float *in, int which, int64_t n, cudaStream_t st);
+int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st, int *launches);
