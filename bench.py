@@ -322,8 +322,8 @@ def main():
     def e2e_step():
         x_d = x_host.to(dev, non_blocking=True)                                   # H2D pixels
         codec.encode(ss, x_d)
-        words, offs, heads, flags = ss.export()                                   # D2H bitstream (+ sizes, heads)
-        ss.import_packed(words, offs, heads)                                      # H2D bitstream (the receiver's side)
+        words, offs, heads = ss.export_packed()                                   # device gather + D2H bitstream, offsets, heads
+        ss.import_packed_fast(words, offs, heads)                                 # H2D + device scatter (the receiver's side)
         o = codec.decode(ss, B, out=out_dev)
         out_host.copy_(o, non_blocking=True)                                      # D2H pixels
         torch.cuda.synchronize()

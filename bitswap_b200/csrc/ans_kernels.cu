@@ -123,6 +123,71 @@ extern "C" int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t
                                 sizeof(uint32_t) * n[i], cudaMemcpyDeviceToHost));
     return BSW_OK;
 }
+// ---- packed (de)serialisation: every stream's words gathered into / scattered from ONE contiguous device buffer with
+// coalesced 128-byte warp accesses, so a host export/import is three memcpys instead of two per stream -------------
+__global__ void k_pack_offsets(const int32_t *__restrict__ n, int count, int64_t *__restrict__ offs) {
+    // single block exclusive scan (count <= a few 10^4 streams)
+    __shared__ long long carry;
+    __shared__ long long part[32];
+    if (threadIdx.x == 0) { carry = 0; offs[0] = 0; }
+    __syncthreads();
+    for (int base = 0; base < count; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        long long v = i < count ? n[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, x, o); if ((threadIdx.x & 31) >= o) x += t; }
+        if ((threadIdx.x & 31) == 31) part[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            long long p = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0, y = p;
+            for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, y, o); if (threadIdx.x >= o) y += t; }
+            part[threadIdx.x] = y - p;
+        }
+        __syncthreads();
+        long long incl = x + part[threadIdx.x >> 5] + carry;
+        if (i < count) offs[i + 1] = incl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = incl;
+        __syncthreads();
+    }
+}
+__global__ void k_pack_words(bsw_streams sv, int first, const int64_t *__restrict__ offs, uint32_t *__restrict__ out,
+                             uint64_t *__restrict__ heads_out) {
+    int b = blockIdx.x;
+    const uint32_t *src = sv.words + (int64_t)(first + b) * sv.cap;
+    int n = sv.nwords[first + b];
+    uint32_t *dst = out + offs[b];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) heads_out[b] = sv.heads[first + b];
+}
+__global__ void k_unpack_words(bsw_streams sv, int first, const int64_t *__restrict__ offs, const uint32_t *__restrict__ in,
+                               const uint64_t *__restrict__ heads_in) {
+    int b = blockIdx.x;
+    uint32_t *dst = sv.words + (int64_t)(first + b) * sv.cap;
+    int64_t o = offs[b];
+    int n = (int)(offs[b + 1] - o);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = in[o + i];
+    if (threadIdx.x == 0) {
+        sv.nwords[first + b] = n; sv.minwords[first + b] = n; sv.heads[first + b] = heads_in[b]; sv.flags[first + b] = 0;
+    }
+}
+extern "C" int bsw_streams_pack(bsw_streams *s, int first, int count, uint32_t *words_dev, int64_t *offsets_dev,
+                                uint64_t *heads_dev, void *stream) {
+    BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B && words_dev && offsets_dev && heads_dev, "bsw_streams_pack: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_pack_offsets<<<1, 1024, 0, st>>>(s->nwords + first, count, offsets_dev);
+    BSW_LAUNCH_CHECK();
+    k_pack_words<<<count, 256, 0, st>>>(*s, first, offsets_dev, words_dev, heads_dev);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+extern "C" int bsw_streams_unpack(bsw_streams *s, int first, int count, const uint32_t *words_dev, const int64_t *offsets_dev,
+                                  const uint64_t *heads_dev, void *stream) {
+    BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B && words_dev && offsets_dev && heads_dev, "bsw_streams_unpack: bad arguments");
+    k_unpack_words<<<count, 256, 0, (cudaStream_t)stream>>>(*s, first, offsets_dev, words_dev, heads_dev);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+
 extern "C" int bsw_streams_device_ptrs(bsw_streams *s, uint32_t **w, int32_t **n, uint64_t **h, int32_t **f) {
     BSW_REQUIRE(s, "null stream set");
     if (w) *w = s->words;

@@ -81,6 +81,57 @@ class StreamSet:
         check(lib().bsw_streams_export(self._h, first, count, words.ctypes.data, offs.ctypes.data))
         return words[:int(offs[-1])], offs, h, f
 
+    # -- fast packed path: one gather/scatter kernel + three memcpys, pinned staging buffers -------------------------
+    def _staging(self, count):
+        import torch
+        st = getattr(self, "_stg", None)
+        need = count * self.capacity
+        if st is None or st["words_d"].numel() < need or st["offs_d"].numel() < count + 1:
+            st = dict(words_d=torch.empty(need, dtype=torch.int32, device="cuda"),
+                      offs_d=torch.empty(count + 1, dtype=torch.int64, device="cuda"),
+                      heads_d=torch.empty(count, dtype=torch.int64, device="cuda"),
+                      words_h=torch.empty(need, dtype=torch.int32).pin_memory(),
+                      offs_h=torch.empty(count + 1, dtype=torch.int64).pin_memory(),
+                      heads_h=torch.empty(count, dtype=torch.int64).pin_memory())
+            self._stg = st
+        return st
+
+    def export_packed(self, first=0, count=None):
+        """(words uint32[sum], offsets int64[count+1], heads uint64[count]) as numpy views of pinned host buffers
+        (valid until the next export_packed/import_packed_fast).  Enqueued on torch's current stream; synchronises it."""
+        import torch
+        from ._lib import cuda_stream_ptr
+        count = self.n - first if count is None else count
+        st = self._staging(count)
+        check(lib().bsw_streams_pack(self._h, first, count, st["words_d"].data_ptr(), st["offs_d"].data_ptr(),
+                                     st["heads_d"].data_ptr(), cuda_stream_ptr()))
+        st["offs_h"][:count + 1].copy_(st["offs_d"][:count + 1], non_blocking=True)
+        st["heads_h"][:count].copy_(st["heads_d"][:count], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        total = int(st["offs_h"][count])
+        st["words_h"][:total].copy_(st["words_d"][:total], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return (st["words_h"][:total].numpy().view(np.uint32), st["offs_h"][:count + 1].numpy(),
+                st["heads_h"][:count].numpy().view(np.uint64))
+
+    def import_packed_fast(self, words, offsets, heads, first=0):
+        """Inverse of export_packed (host arrays -> device scatter). Async on torch's current stream."""
+        import torch
+        from ._lib import cuda_stream_ptr
+        count = len(heads)
+        total = int(offsets[count])
+        assert int(np.max(np.diff(offsets))) <= self.capacity
+        st = self._staging(count)
+        if words.ctypes.data != st["words_h"].data_ptr():
+            st["words_h"][:total].copy_(torch.from_numpy(np.ascontiguousarray(words).view(np.int32)))
+            st["offs_h"][:count + 1].copy_(torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)))
+            st["heads_h"][:count].copy_(torch.from_numpy(np.ascontiguousarray(heads).view(np.int64)))
+        st["words_d"][:total].copy_(st["words_h"][:total], non_blocking=True)
+        st["offs_d"][:count + 1].copy_(st["offs_h"][:count + 1], non_blocking=True)
+        st["heads_d"][:count].copy_(st["heads_h"][:count], non_blocking=True)
+        check(lib().bsw_streams_unpack(self._h, first, count, st["words_d"].data_ptr(), st["offs_d"].data_ptr(),
+                                       st["heads_d"].data_ptr(), cuda_stream_ptr()))
+
     def export_lists(self, first=0, count=None):
         words, offs, heads, flags = self.export(first, count)
         return [[int(v) for v in words[offs[i]:offs[i + 1]]] + [int(heads[i])] for i in range(len(heads))]

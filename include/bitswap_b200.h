@@ -72,6 +72,13 @@ int bsw_streams_sizes(bsw_streams *s, int64_t *nwords_host, uint64_t *heads_host
 int bsw_streams_min_words(bsw_streams *s, int64_t *min_host);
 /* Packed export: stream i's words go to words_host[offsets_host[i] ...). Synchronous. */
 int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t *words_host, const int64_t *offsets_host);
+/* Device-side packed (de)serialisation, async on `stream`: all streams' words gathered into one contiguous device
+ * buffer (capacity >= total words; offsets_dev holds count+1 int64 prefix sums, heads_dev count uint64), or scattered back
+ * (unpack requires every stream's length <= capacity; it also resets flags).  A host export is then three memcpys. */
+int bsw_streams_pack(bsw_streams *s, int first, int count, uint32_t *words_dev, int64_t *offsets_dev, uint64_t *heads_dev,
+                     void *stream);
+int bsw_streams_unpack(bsw_streams *s, int first, int count, const uint32_t *words_dev, const int64_t *offsets_dev,
+                       const uint64_t *heads_dev, void *stream);
 /* Raw device views for device-resident pipelines (NCCL gathers, custom kernels). */
 int bsw_streams_device_ptrs(bsw_streams *s, uint32_t **words_dev, int32_t **nwords_dev, uint64_t **heads_dev,
                             int32_t **flags_dev);

@@ -284,3 +284,25 @@ def test_cdf_fast_equals_exact():
     ex = (ctypes.c_double * 5)()
     check(lib().bsw_selftest_cdf(1 << 27, 12345, ctypes.byref(bad), ex))
     assert bad.value == 0, f"{bad.value} mismatches, e.g. (e, mu, sigma, fast, exact) = {list(ex)}"
+
+
+def test_packed_export_import_roundtrip():
+    """Device gather/scatter serialisation == the per-stream export, and import restores every stream."""
+    B = 37
+    ss = StreamSet(B, 512)
+    rs = np.random.RandomState(3)
+    states = []
+    for b in range(B):
+        n = int(rs.randint(0, 500))
+        states.append([int(v) for v in rs.randint(0, 1 << 32, size=n, dtype=np.uint64)] + [int(rs.randint(1 << 32, 1 << 62))])
+    ss.import_lists(states)
+    w, o, h = ss.export_packed()
+    w2, o2, h2, _ = ss.export()
+    assert np.array_equal(w, w2) and np.array_equal(o, o2) and np.array_equal(h, h2)
+    w, o, h = w.copy(), o.copy(), h.copy()
+    ss2 = StreamSet(B, 512)
+    ss2.import_packed_fast(w, o, h)
+    torch.cuda.synchronize()
+    assert ss2.export_lists() == states
+    sub_w, sub_o, sub_h = ss.export_packed(first=5, count=9)
+    assert np.array_equal(sub_o, o[5:15] - o[5]) and np.array_equal(sub_w, w[o[5]:o[14]])
