@@ -234,3 +234,22 @@ if __name__ == "__main__":
         model_golden(n)
         bitswap_golden(n)
     print("golden files written to", OUT)
+
+
+def logp_golden():
+    """Reference log-densities (utils/torch/rand.py:23-64) on random inputs incl. edge pixels and vanishing bins."""
+    from utils.torch.rand import logistic_logp, discretized_logistic_logp
+    rs = np.random.RandomState(21)
+    mu = torch.from_numpy(rs.normal(0, 1.5, (3, 4, 50))); sc = torch.from_numpy(rs.uniform(0.1, 1.0, (3, 4, 50)))
+    x = torch.from_numpy(rs.normal(0, 2, (3, 4, 50)))
+    lp = logistic_logp(mu, sc, x)
+    xm = torch.from_numpy(rs.uniform(-1, 1, (5, 300))); xs = torch.from_numpy(rs.uniform(0.002, 0.7, (5, 300)))
+    xx = torch.from_numpy(rs.randint(0, 256, (5, 300)).astype(np.float64)); xx[0, :6] = torch.tensor([0, 255, 0, 255, 1, 254.])
+    xs[1, :40] = 1e-4
+    dl = discretized_logistic_logp(xm, xs, xx)
+    np.savez_compressed(os.path.join(OUT, "logp.npz"), mu=mu.numpy(), sc=sc.numpy(), x=x.numpy(), lp=lp.numpy(),
+                        xm=xm.numpy(), xs=xs.numpy(), xx=xx.numpy(), dl=dl.numpy())
+
+
+if __name__ == "__main__":
+    logp_golden()
