@@ -79,7 +79,7 @@ def sigmoids(cfg):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), B=1024
-TRAFFIC = {"rows_z": 33.7e6 + 234.2e6, "pop_z": 321.0e6 + 7.5e6, "conv_dense3x3": 542.6e6 + 235.3e6}
+TRAFFIC = {"rows_z": 36.0e6 + 234.3e6, "pop_z": 321.0e6 + 9.2e6, "conv_dense3x3": 543.4e6 + 234.8e6}    # profiles/r1_ncu_{rows_v3,popcoarse_v2,convtc_v2}.md
 
 
 # ----------------------------------------------------------------------------------------------------
