@@ -3,7 +3,7 @@
 Reference: Model.loss (model/cifar_train.py:441-490) as used by the compression scripts for the
 "net bits - ELBO" gap (cifar_compress.py:169-173,258,262), with the log-densities of utils/torch/rand.py:23-64.
 Works with any object exposing infer(i)(given) / generate(i)(given) on flat [B, dim] inputs in compressing mode
-(bitswap_b200.model.Model on the GPU; the torch oracle in the tests).
+(bitswap_b200.model.Model on the GPU; a torch-CPU restatement of the nets in the tests).
 """
 import math
 
