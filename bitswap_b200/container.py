@@ -48,10 +48,15 @@ def compress_images(codec, images, excess_state_len=10000, seed=100, scheme=BITS
     ss = StreamSet(n, excess_state_len + 1400 * max(nblk) + 64)
     w, head = initial_words(excess_state_len, seed=seed)
     ss.fill(w, head)
+    # all blocks to the device once: [step t, stream j] = block t of the j-th largest image (CHW, demo_compress.py:120)
+    C = tiled[order[0]][0].shape[-1]
+    host = np.zeros((max(nblk), n, C, 32, 32), dtype=np.uint8)
+    for j, i in enumerate(order):
+        host[:nblk[j], j] = tiled[i][0].transpose(0, 3, 1, 2)
+    dev = torch.from_numpy(host).cuda()
     for t in range(max(nblk)):
         active = sum(1 for b in nblk if b > t)
-        x = np.stack([tiled[order[j]][0][t] for j in range(active)]).transpose(0, 3, 1, 2)     # -> CHW (demo_compress.py:120)
-        codec.encode(ss, torch.from_numpy(np.ascontiguousarray(x)).cuda(), first=0, scheme=scheme)
+        codec.encode(ss, dev[t, :active].contiguous(), first=0, scheme=scheme)
     torch.cuda.synchronize()
     ss.raise_on_error()
     words, offs, heads, _ = ss.export()
@@ -79,12 +84,12 @@ def decompress_images(codec, containers, channels=3, scheme=BITSWAP):
     n = len(containers)
     ss = StreamSet(n, max(len(meta[i][0]) for i in order) + 64)
     ss.import_lists([[int(v) for v in meta[i][0]] + [meta[i][1]] for i in order])
-    blocks = [np.zeros((b, 32, 32, channels), dtype=np.uint8) for b in nblk]
+    dev = torch.zeros((max(nblk), n, channels, 32, 32), dtype=torch.uint8, device="cuda")
     for t in reversed(range(max(nblk))):
         active = sum(1 for b in nblk if b > t)
-        x = codec.decode(ss, active, first=0, scheme=scheme).cpu().numpy().transpose(0, 2, 3, 1)
-        for j in range(active):
-            blocks[j][t] = x[j]
+        dev[t, :active] = codec.decode(ss, active, first=0, scheme=scheme)
+    host = dev.cpu().numpy()                                               # one transfer for every block of every image
+    blocks = [np.ascontiguousarray(host[:nblk[j], j].transpose(0, 2, 3, 1)) for j in range(n)]
     ss.raise_on_error()
     out = [None] * n
     for j, i in enumerate(order):
