@@ -15,6 +15,7 @@
 //            float64 function (bit-identical by construction) and finishes the search with a warp scan.
 //
 // Results are bit-identical to the fused kernels (integer sums are associative; the cdf function is shared).
+#include <stdlib.h>
 #include "bsw_common.cuh"
 
 #define FULL 0xffffffffu
@@ -85,24 +86,59 @@ constexpr int RW = 16;       // warps per CTA in phase A: 512 threads x <=64 reg
 // cdf of the previous bin is already in a register (one shuffle per row instead of two per bin) and the 32-bin chunk
 // totals the pop side needs are lane-local sums (no per-chunk warp reduction).  ~42 issued instructions per cdf value,
 // 27 of them on the FP64 pipe.
-template <int NB>
-__device__ __forceinline__ int tile_idx2(int k) { return k + k / NB; }       // conflict-free for lane-blocked 8-byte reads
+// Tile layout: lane l's NB endpoints are contiguous and start at double index l*(NB+PAD).  PAD = 2 keeps every chunk
+// 16-byte aligned (a TMA bulk-copy requirement) at the price of a 2-way bank conflict on the lane-blocked 8-byte reads
+// (one LDS per cdf value against 27 FP64 instructions: irrelevant).  NB = 1 rows (S = 32) are too small for bulk copies
+// and use plain loads.
+template <int NB, bool USE_TMA>
+struct RowTile {
+    static constexpr bool TMA = USE_TMA && NB >= 2;
+    static constexpr int PAD = TMA ? 2 : 1;              // plain staging: odd stride, conflict-free
+    static constexpr int STRIDE = NB + PAD;
+    static constexpr int DOUBLES = 32 * STRIDE;
+};
 
-template <int NB, bool POP>
+__device__ __forceinline__ uint32_t smem_u32r(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try_wait_r(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32r(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <int NB, bool POP, bool USE_TMA>
 __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint2 *__restrict__ pairs, uint32_t *__restrict__ coarse,
         uint2 *__restrict__ fix) {
     constexpr int S = 32 * NB;
-    __shared__ double tile[S + 32];
+    using RT = RowTile<NB, USE_TMA>;
+    __shared__ __align__(16) double tile[RT::DOUBLES];
+    __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = blockIdx.x;                      // row index i within the level
     const int si = blockIdx.y * RW + warp;               // stream
-    {
-        const double *e = endp + row * ers;
-        for (int k = threadIdx.x; k < S; k += RW * 32) tile[tile_idx2<NB>(k)] = __ldg(e + k);
+    const double *e = endp + row * ers;
+    if (RT::TMA) {
+        // TMA-staged endpoint tile: 32 bulk copies (one per lane-chunk, NB*8 bytes each) complete on one mbarrier
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32r(&bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32r(&bar)), "r"((uint32_t)(S * 8)) : "memory");
+            __syncwarp();
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32r(tile + lane * RT::STRIDE)), "l"(e + lane * NB), "r"((uint32_t)(NB * 8)), "r"(smem_u32r(&bar)) : "memory");
+        }
+        uint32_t spins = 0;
+        while (!mbar_try_wait_r(&bar, 0)) { if (++spins > (1u << 22)) __trap(); }
+    } else {
+        for (int k = threadIdx.x; k < S; k += RW * 32) tile[(k / NB) * RT::STRIDE + (k % NB)] = __ldg(e + k);
+        __syncthreads();
     }
-    __syncthreads();
     if (si >= count) return;
     const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];
     const double rs = __ddiv_rn(1.0, s);
@@ -113,7 +149,7 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
 
     BswExpRegs K;
     K.load();
-    const double *my = tile + lane * (NB + 1);
+    const double *my = tile + lane * RT::STRIDE;
     // cdf at my last endpoint first: the next lane needs it as the lower neighbour of its first bin.  The row's very
     // last entry is the +1e300 pad: t clamps to +690 and the cdf comes out as exactly 1.0, the reference's
     // `1. - cdfs[:,-1]` upper bound of the last bin (cifar_compress.py:184).
@@ -281,9 +317,19 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
     uint2 *pairs = (uint2 *)scratch;
     uint32_t *coarse = (uint32_t *)scratch;
     uint2 *fix = (uint2 *)((uint8_t *)scratch + (size_t)count * L * NB * 4);
+    // Endpoint-row staging: plain coalesced loads into a conflict-free padded tile (default), or 32 TMA bulk copies
+    // completing on an mbarrier (BSW_ROWS_TMA=1).  Measured on B200, C8, 1024 streams: 4.53 ms vs 5.40 ms per z level --
+    // 256-byte bulk copies are too small to beat two in-flight loads per thread, so TMA staging is the documented option,
+    // not the default.
+    static const bool tma = getenv("BSW_ROWS_TMA") && getenv("BSW_ROWS_TMA")[0] == '1';
     if (phase == 0) {
-        if (pop) k_rows<NB, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix);
-        else k_rows<NB, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr);
+        if (pop) {
+            if (tma) k_rows<NB, true, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix);
+            else k_rows<NB, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix);
+        } else {
+            if (tma) k_rows<NB, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr);
+            else k_rows<NB, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr);
+        }
     } else {
         if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
         else k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pairs, L, bits);
