@@ -472,3 +472,42 @@ def test_elbo_on_gpu_nets_matches_oracle_nets():
     b = elbo(orc, x, cfg=cfg, eps=eps)
     assert (a["elbo_bits_per_dim"].cpu() - b["elbo_bits_per_dim"]).abs().max() < 1e-3
     print("ELBO bits/dim (random-init tiny3):", a["elbo_bits_per_dim"].cpu().numpy().round(3))
+
+
+def test_p4_cifar8_full_size_vs_oracle_and_batch_roundtrip():
+    """BASELINE.json configs[1] at full size (CIFAR nz=8, W=252, q=10, tensor-core nets, pipelined codec):
+    (a) stream 0 of a 40-stream batch == the CPU oracle recursion driven with the same GPU nets, bit for bit
+        (35 840 symbol-ops, 15 data-dependent 2048x1024 tables + the x table + the prior);
+    (b) size-independent properties on the whole batch: identical inputs -> identical streams, exact pixel round
+        trip, initial states restored, per-stream flags clean."""
+    from bitswap_b200.codec import PipelinedCodec
+    cfg = preset("cifar8")
+    B = 40
+    sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=False)
+    zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    pc = PipelinedCodec(cfg, sd, Bins(cfg, zend, zcen), B, lanes=3, use_tensor_cores=True)
+    imgs = synthetic.synthetic_images(cfg, B, seed=77)
+    imgs[1] = imgs[0]                                           # streams 0 and 1: same image, same initial state
+    ss = StreamSet(B, 8192)
+    w, head = synthetic.initial_words(4096, seed=100)
+    ss.fill(w, head)
+    init = ss.export_lists()
+    pc.encode(ss, torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    ss.raise_on_error()
+    got = ss.export_lists()
+    assert got[0] == got[1] and got[0] != got[2]
+    m = pc.models[0]
+    orc = O.BitSwapOracle(cfg, O.ModelOracle(cfg, sd), zend, zcen, coder="c", pmf="c")
+
+    def gpu_net(kind, level, given):
+        f = m.infer(level) if kind == "infer" else m.generate(level)
+        mu, sc = f(given.cuda())
+        return mu.cpu(), sc.cpu()
+    orc._net = gpu_net
+    want = orc.encode_image(O.CState(w, head), imgs[0]).to_list()
+    assert got[0] == want, "full-size stream differs from the CPU oracle"
+    out = pc.decode(ss, B)
+    torch.cuda.synchronize()
+    ss.raise_on_error()
+    assert np.array_equal(out.cpu().numpy(), imgs) and ss.export_lists() == init
