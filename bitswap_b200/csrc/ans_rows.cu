@@ -110,7 +110,7 @@ template <int NB, bool POP, bool USE_TMA>
 __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint2 *__restrict__ pairs, uint32_t *__restrict__ coarse,
-        uint2 *__restrict__ fix) {
+        uint2 *__restrict__ fix, uint32_t *__restrict__ pfull) {
     constexpr int S = 32 * NB;
     using RT = RowTile<NB, USE_TMA>;
     __shared__ __align__(16) double tile[RT::DOUBLES];
@@ -158,25 +158,46 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     double prev = lane == 0 ? 0.0 : up;
     uint32_t lsum = 0, lbest = 0, pre = 0, pv = 0;
     int lbi = 0;
-#pragma unroll 4
-    for (int j = 0; j < NB - 1; ++j) {
-        const double c = bsw_cdf_fast_regs(my[j], m, s, rs, K);
-        const uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;      // :29 trunc, :32 +1
-        prev = c;
+    // pop, small batches: also keep every integer pmf of the row (before the remnant) so that the serial phase needs no
+    // float64 work at all (k_pop_full); written as one 16-byte store per 4 bins
+    constexpr int G = NB >= 4 ? 4 : NB;                  // bins per group
+    uint32_t *prow = (POP && pfull) ? pfull + ((int64_t)si * L + row) * S + lane * NB : nullptr;
+    auto account = [&](uint32_t v, int j) {
         lsum += v;
         if (v > lbest) { lbest = v; lbi = j; }
         if (!POP) {
             pre += (j < js) ? v : 0u;
             if (j == js) pv = v;
         }
+    };
+#pragma unroll 1
+    for (int j0 = 0; j0 < NB - G; j0 += G) {
+        uint32_t vv[G];
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            const double c = bsw_cdf_fast_regs(my[j0 + t], m, s, rs, K);
+            vv[t] = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;            // :29 trunc, :32 +1
+            prev = c;
+            account(vv[t], j0 + t);
+        }
+        if (POP && prow) {
+            if (G == 4) *reinterpret_cast<uint4 *>(prow + j0) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+            else for (int t = 0; t < G; ++t) prow[j0 + t] = vv[t];
+        }
     }
-    {
-        const uint32_t v = __double2uint_rz(__dmul_rn(__dsub_rn(c_last, prev), mult)) + 1u;
-        lsum += v;
-        if (v > lbest) { lbest = v; lbi = NB - 1; }
-        if (!POP) {
-            pre += (NB - 1 < js) ? v : 0u;
-            if (NB - 1 == js) pv = v;
+    {   // last group: its last bin is the lane's last bin, whose cdf is already known
+        uint32_t vv[G];
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            const int j = NB - G + t;
+            const double c = (t == G - 1) ? c_last : bsw_cdf_fast_regs(my[j], m, s, rs, K);
+            vv[t] = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;
+            prev = c;
+            account(vv[t], j);
+        }
+        if (POP && prow) {
+            if (G == 4) *reinterpret_cast<uint4 *>(prow + NB - G) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+            else for (int t = 0; t < G; ++t) prow[NB - G + t] = vv[t];
         }
     }
     uint32_t incl = lsum;
@@ -309,14 +330,83 @@ __global__ void __launch_bounds__(BW * 32) k_pop_coarse(bsw_streams sv, int firs
     ws.close(sv, b, lane);
 }
 
+// ---- phase B: pop from the full integer table (small batches) --------------------------------------------------------
+// Same search as k_pop_coarse, but the 32 integer pmfs of the chosen chunk are read back from phase A's table instead of
+// being recomputed: no float64 on the serial path (per row: coarse cdf [prefetched] -> ballot -> one 128-byte load ->
+// warp scan -> ballot -> decode).
+template <int NB>
+__global__ void __launch_bounds__(BW * 32) k_pop_full(bsw_streams sv, int first, int count, const uint32_t *__restrict__ pfull,
+        const uint32_t *__restrict__ coarse, const uint2 *__restrict__ fix, int16_t *__restrict__ sym, int64_t L, int bits) {
+    const int lane = threadIdx.x & 31;
+    const int si = blockIdx.x * BW + (threadIdx.x >> 5);
+    if (si >= count) return;
+    const int b = first + si;
+    WarpStream2 ws;
+    ws.open(sv, b);
+    if (ws.err) return;
+    constexpr int S = 32 * NB;
+    const uint32_t *cb = coarse + (int64_t)si * L * NB;
+    const uint32_t *pb = pfull + (int64_t)si * L * S;
+    const uint2 *fb = fix + (int64_t)si * L;
+    int16_t *sy = sym + (int64_t)si * L;
+    const uint32_t mask = (uint32_t)(((uint64_t)1 << bits) - 1);
+    uint2 fx_w = make_uint2(0, 0), fx_nx;
+    int my_sym = 0;
+    {
+        int64_t r = ((L - 1) & ~(int64_t)31) + lane;
+        fx_nx = r < L ? __ldg(fb + r) : make_uint2(0, 0);
+    }
+    uint32_t base_n1 = (lane < NB) ? __ldg(cb + (L - 1) * NB + lane) : 0xffffffffu;
+    uint32_t base_n2 = (lane < NB && L > 1) ? __ldg(cb + (L - 2) * NB + lane) : 0xffffffffu;
+    for (int64_t i = L - 1; i >= 0; --i) {
+        const int j32 = (int)(i & 31);
+        const bool new_block = (j32 == 31 || i == L - 1);
+        if (new_block) fx_w = fx_nx;
+        const int bi = (int)__shfl_sync(FULL, fx_w.x, j32);
+        const uint32_t rem = __shfl_sync(FULL, fx_w.y, j32);
+        if (new_block) {
+            int64_t r = (i & ~(int64_t)31) - 32 + lane;
+            fx_nx = r >= 0 ? __ldg(fb + r) : make_uint2(0, 0);
+        }
+        const uint32_t base = base_n1;
+        base_n1 = base_n2;
+        if (i > 1) base_n2 = (lane < NB) ? __ldg(cb + (i - 2) * NB + lane) : 0xffffffffu;
+        const uint32_t mm = (uint32_t)ws.x & mask;                                       // cifar_compress.py:60
+        const int chunk = 31 - __clz(__ballot_sync(FULL, base <= mm));
+        const int k = chunk * 32 + lane;
+        uint32_t v = __ldg(pb + i * S + k) + (k == bi ? rem : 0u);
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t cex = __shfl_sync(FULL, base, chunk) + incl - v;
+        const int js = 31 - __clz(__ballot_sync(FULL, cex <= mm));                       // :61
+        const uint32_t ps = __shfl_sync(FULL, v, js), cs = __shfl_sync(FULL, cex, js);
+        if (lane == j32) my_sym = chunk * 32 + js;                                       // :62
+        ws.decode(ps, cs, mm, bits, lane);                                               // :63-65
+        if (j32 == 0 || ws.err) {
+            int64_t r = (i & ~(int64_t)31) + lane;
+            if (r < L && r >= i) sy[r] = (int16_t)my_sym;
+            if (ws.err) break;
+        }
+    }
+    ws.close(sv, b, lane);
+}
+
 template <int NB>
 int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
                 int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int bits, int q, void *scratch,
-                cudaStream_t st) {
+                size_t scratch_bytes, cudaStream_t st) {
+    constexpr int S = 32 * NB;
     dim3 grid((unsigned)L, (count + RW - 1) / RW);
+    // pop scratch layout: [full table: count*L*S u32 (only if it fits)] [coarse: count*L*NB u32] [fix: count*L uint2]
+    const size_t full_bytes = (size_t)count * L * S * 4, small_bytes = (size_t)count * L * NB * 4 + (size_t)count * L * 8;
+    const bool full = pop && NB >= 4 && scratch_bytes >= full_bytes + small_bytes;
     uint2 *pairs = (uint2 *)scratch;
-    uint32_t *coarse = (uint32_t *)scratch;
-    uint2 *fix = (uint2 *)((uint8_t *)scratch + (size_t)count * L * NB * 4);
+    uint32_t *pfull = full ? (uint32_t *)scratch : nullptr;
+    uint32_t *coarse = (uint32_t *)((uint8_t *)scratch + (full ? full_bytes : 0));
+    uint2 *fix = (uint2 *)((uint8_t *)coarse + (size_t)count * L * NB * 4);
     // Endpoint-row staging: plain coalesced loads into a conflict-free padded tile (default), or 32 TMA bulk copies
     // completing on an mbarrier (BSW_ROWS_TMA=1).  Measured on B200, C8, 1024 streams: 4.53 ms vs 5.40 ms per z level --
     // 256-byte bulk copies are too small to beat two in-flight loads per thread, so TMA staging is the documented option,
@@ -324,14 +414,15 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
     static const bool tma = getenv("BSW_ROWS_TMA") && getenv("BSW_ROWS_TMA")[0] == '1';
     if (phase == 0) {
         if (pop) {
-            if (tma) k_rows<NB, true, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix);
-            else k_rows<NB, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix);
+            if (tma) k_rows<NB, true, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
+            else k_rows<NB, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
         } else {
-            if (tma) k_rows<NB, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr);
-            else k_rows<NB, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr);
+            if (tma) k_rows<NB, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
+            else k_rows<NB, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
         }
     } else {
-        if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
+        if (pop && full) k_pop_full<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits);
+        else if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
         else k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pairs, L, bits);
     }
     BSW_LAUNCH_CHECK();
@@ -340,28 +431,32 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
 
 }  // namespace
 
-// Scratch bytes needed by the two-phase coder for `count` streams of L rows with support S.
-size_t bsw_rows_scratch_bytes(int count, int64_t L, int S) {
-    size_t pop = (size_t)count * L * (S / 32) * 4 + (size_t)count * L * 8;
+// Scratch bytes for the two-phase coder for `count` streams of L rows with support S: `full` adds room for the whole
+// integer pmf table, which lets the serial pop phase skip its float64 recomputation (used when it fits the budget).
+size_t bsw_rows_scratch_bytes(int count, int64_t L, int S, bool full) {
+    size_t small = (size_t)count * L * (S / 32) * 4 + (size_t)count * L * 8;
     size_t push = (size_t)count * L * 8;
+    size_t pop = small + (full ? (size_t)count * L * S * 4 : 0);
     return pop > push ? pop : push;
 }
 
 // Two-phase variants of bsw_logistic_push / bsw_logistic_pop (same arguments + caller-provided scratch).
-// phase 0 = the parallel row-table kernel, phase 1 = the serial coder; call both, in order, on one stream.
+// phase 0 = the parallel row-table kernel, phase 1 = the serial coder; call both, in order, on one stream, with the
+// same scratch and scratch_bytes (the pop path picks the full-table variant when the scratch is large enough).
 int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
                     int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
-                    void *scratch, cudaStream_t st) {
+                    void *scratch, size_t scratch_bytes, cudaStream_t st) {
     BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B, "stream range out of bounds");
     BSW_REQUIRE(mu && sc && endp && sym && scratch && L > 0 && L < 65536 * 32, "two-phase coder: bad arguments");
-    BSW_REQUIRE(ers == 0 || ers >= S, "two-phase coder: endpoint rows must hold S doubles (+inf padded)");
+    BSW_REQUIRE(ers == 0 || ers >= S, "two-phase coder: endpoint rows must hold S doubles (+1e300 padded)");
+    BSW_REQUIRE(scratch_bytes >= bsw_rows_scratch_bytes(count, L, S, false), "two-phase coder: scratch too small");
     switch (S) {
-        case 32:   return launch_rows<1>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
-        case 64:   return launch_rows<2>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
-        case 128:  return launch_rows<4>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
-        case 256:  return launch_rows<8>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
-        case 512:  return launch_rows<16>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
-        case 1024: return launch_rows<32>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 32:   return launch_rows<1>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
+        case 64:   return launch_rows<2>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
+        case 128:  return launch_rows<4>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
+        case 256:  return launch_rows<8>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
+        case 512:  return launch_rows<16>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
+        case 1024: return launch_rows<32>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
     }
     bsw_set_error("two-phase coder: support must be one of 32,64,...,1024 (got %d)", S);
     return BSW_E_INVALID;

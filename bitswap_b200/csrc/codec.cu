@@ -18,7 +18,8 @@ struct bsw_codec {
     int16_t *sym[2];                    // ping-pong latent symbols [max_batch, zdim]
     int16_t *xsym;                      // [max_batch, xdim] pixels as int16 symbols
     std::vector<int16_t *> zs;          // BB-ANS: all nz latents
-    void *scratch;                      // two-phase coder: pairs / coarse cdf of one level
+    void *scratch;                      // two-phase coder: pairs / coarse cdf (/ full integer table) of one level
+    size_t scratch_bytes;
     int two_phase;                      // 1: ans_rows.cu path (default), 0: fused one-warp-per-stream kernels
     uint32_t *priorP, *priorC;          // Logistic(0,1) prior tables over zendpoints[-1], shared by all streams
     int64_t launches;
@@ -37,10 +38,10 @@ int bsw_ans_push_i16(bsw_streams *s, int first, int count, const uint32_t *P, co
 int bsw_ans_pop_i16(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *C, int64_t pss, int64_t css,
                     int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
 
-size_t bsw_rows_scratch_bytes(int count, int64_t L, int S);
+size_t bsw_rows_scratch_bytes(int count, int64_t L, int S, bool full);
 int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
                     int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
-                    void *scratch, cudaStream_t st);
+                    void *scratch, size_t scratch_bytes, cudaStream_t st);
 
 __global__ void k_u8_to_i16(const uint8_t *__restrict__ in, int16_t *__restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,8 +69,14 @@ extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int 
     BSW_CUDA(cudaMalloc(&c->xsym, sizeof(int16_t) * c->xdim * max_batch));
     c->zs.assign(c->nz, nullptr);
     {
-        size_t a = bsw_rows_scratch_bytes(max_batch, c->zdim, c->S), b2 = bsw_rows_scratch_bytes(max_batch, c->xdim, 256);
-        BSW_CUDA(cudaMalloc(&c->scratch, a > b2 ? a : b2));
+        // room for the full integer tables when that stays under FULL_BUDGET (small batches / pipelined lanes): the serial
+        // pop phase then needs no float64 recomputation
+        const size_t FULL_BUDGET = (size_t)3 << 30;
+        size_t a = bsw_rows_scratch_bytes(max_batch, c->zdim, c->S, false), b2 = bsw_rows_scratch_bytes(max_batch, c->xdim, 256, false);
+        size_t af = bsw_rows_scratch_bytes(max_batch, c->zdim, c->S, true), bf = bsw_rows_scratch_bytes(max_batch, c->xdim, 256, true);
+        size_t small = a > b2 ? a : b2, big = af > bf ? af : bf;
+        c->scratch_bytes = big <= FULL_BUDGET ? big : small;
+        BSW_CUDA(cudaMalloc(&c->scratch, c->scratch_bytes));
         c->two_phase = 1;
     }
     // prior tables: Logistic(0,1) over the top level's endpoints, identical for every stream and image
@@ -185,11 +192,11 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_Z, st);
-        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
+        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         c->prof.begin(CAT_POP_Z, st);
-        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
+        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }
@@ -204,11 +211,11 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_Z, st);
-        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
+        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         c->prof.begin(CAT_PUSH_Z, st);
-        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, st);
+        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }
@@ -225,11 +232,11 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_X, st);
-        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
+        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         c->prof.begin(CAT_POP_X, st);
-        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
+        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }
@@ -244,11 +251,11 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_X, st);
-        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
+        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         c->prof.begin(CAT_PUSH_X, st);
-        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, st);
+        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }
