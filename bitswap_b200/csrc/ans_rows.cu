@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(BW * 32) k_pop_coarse(bsw_streams sv, int firs
 // warp scan -> ballot -> decode).
 template <int NB>
 __global__ void __launch_bounds__(BW * 32) k_pop_full(bsw_streams sv, int first, int count, const uint32_t *__restrict__ pfull,
-        const uint32_t *__restrict__ coarse, const uint2 *__restrict__ fix, int16_t *__restrict__ sym, int64_t L, int bits) {
+        const uint32_t *__restrict__ coarse, const uint2 *__restrict__ fix, int16_t *__restrict__ sym, int64_t L, int bits,
+        int shared_tables) {
     const int lane = threadIdx.x & 31;
     const int si = blockIdx.x * BW + (threadIdx.x >> 5);
     if (si >= count) return;
@@ -345,9 +346,10 @@ __global__ void __launch_bounds__(BW * 32) k_pop_full(bsw_streams sv, int first,
     ws.open(sv, b);
     if (ws.err) return;
     constexpr int S = 32 * NB;
-    const uint32_t *cb = coarse + (int64_t)si * L * NB;
-    const uint32_t *pb = pfull + (int64_t)si * L * S;
-    const uint2 *fb = fix + (int64_t)si * L;
+    const int64_t ts = shared_tables ? 0 : si;            // one table set for every stream (the prior) or one per stream
+    const uint32_t *cb = coarse + ts * L * NB;
+    const uint32_t *pb = pfull + ts * L * S;
+    const uint2 *fb = fix + ts * L;
     int16_t *sy = sym + (int64_t)si * L;
     const uint32_t mask = (uint32_t)(((uint64_t)1 << bits) - 1);
     uint2 fx_w = make_uint2(0, 0), fx_nx;
@@ -421,7 +423,7 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
             else k_rows<NB, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
         }
     } else {
-        if (pop && full) k_pop_full<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits);
+        if (pop && full) k_pop_full<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, 0);
         else if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
         else k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pairs, L, bits);
     }
@@ -430,6 +432,38 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
 }
 
 }  // namespace
+
+// Pop from ONE materialised table shared by every stream (the Logistic(0,1) prior): P [L][S] with the remnant already
+// applied, coarse[L][S/32] = C[i][32 r], fix = zeros.
+__global__ void k_coarse_from_cdf(const uint32_t *__restrict__ C, int64_t L, int S, uint32_t *__restrict__ coarse, uint2 *__restrict__ fix) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int nb = S / 32;
+    if (i >= L * nb) return;
+    int64_t row = i / nb;
+    int r = (int)(i - row * nb);
+    coarse[i] = C[row * (S + 1) + 32 * r];
+    if (r == 0) fix[row] = make_uint2(0xffffffffu, 0u);
+}
+int bsw_prior_coarse(const uint32_t *C, int64_t L, int S, uint32_t *coarse, uint2 *fix, cudaStream_t st) {
+    int64_t n = L * (S / 32);
+    k_coarse_from_cdf<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(C, L, S, coarse, fix);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+int bsw_pop_shared_table(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *coarse, const uint2 *fix,
+                         int16_t *sym, int64_t L, int S, int bits, cudaStream_t st) {
+    BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B, "stream range out of bounds");
+    dim3 grid((count + BW - 1) / BW);
+    switch (S) {
+        case 128:  k_pop_full<4><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
+        case 256:  k_pop_full<8><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
+        case 512:  k_pop_full<16><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
+        case 1024: k_pop_full<32><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
+        default: return BSW_E_INVALID;
+    }
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
 
 // Scratch bytes for the two-phase coder for `count` streams of L rows with support S: `full` adds room for the whole
 // integer pmf table, which lets the serial pop phase skip its float64 recomputation (used when it fits the budget).

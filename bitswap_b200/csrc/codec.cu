@@ -21,7 +21,9 @@ struct bsw_codec {
     void *scratch;                      // two-phase coder: pairs / coarse cdf (/ full integer table) of one level
     size_t scratch_bytes;
     int two_phase;                      // 1: ans_rows.cu path (default), 0: fused one-warp-per-stream kernels
-    uint32_t *priorP, *priorC;          // Logistic(0,1) prior tables over zendpoints[-1], shared by all streams
+    uint32_t *priorP, *priorC;
+    uint32_t *priorCoarse = nullptr;    // prior cdf at every 32nd bin + dummy fix: lets the prior pop use k_pop_full
+    uint2 *priorFix = nullptr;          // Logistic(0,1) prior tables over zendpoints[-1], shared by all streams
     int64_t launches;
     BswProf prof;
     // overlap: convs go to a high-priority internal stream, coder kernels to a low-priority one, chained by events, so
@@ -39,6 +41,9 @@ int bsw_ans_pop_i16(bsw_streams *s, int first, int count, const uint32_t *P, con
                     int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
 
 size_t bsw_rows_scratch_bytes(int count, int64_t L, int S, bool full);
+int bsw_prior_coarse(const uint32_t *C, int64_t L, int S, uint32_t *coarse, uint2 *fix, cudaStream_t st);
+int bsw_pop_shared_table(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *coarse, const uint2 *fix,
+                         int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
 int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
                     int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
                     void *scratch, size_t scratch_bytes, cudaStream_t st);
@@ -88,6 +93,11 @@ extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int 
     BSW_CUDA(cudaMemcpy(dms, ms, sizeof(ms), cudaMemcpyHostToDevice));
     const double *zend = b->zend + (size_t)(c->nz - 1) * c->zdim * c->S;
     int rc = bsw_logistic_tables(zend, c->S, dms, dms + 1, 0, c->zdim, c->S, 31, c->q, c->priorP, c->priorC, nullptr);
+    if (!rc && c->S >= 128) {
+        BSW_CUDA(cudaMalloc(&c->priorCoarse, sizeof(uint32_t) * (size_t)c->zdim * (c->S / 32)));
+        BSW_CUDA(cudaMalloc(&c->priorFix, sizeof(uint2) * (size_t)c->zdim));
+        rc = bsw_prior_coarse(c->priorC, c->zdim, c->S, c->priorCoarse, c->priorFix, nullptr);
+    }
     BSW_CUDA(cudaDeviceSynchronize());
     cudaFree(dms);
     if (rc) return rc;
@@ -106,7 +116,7 @@ extern "C" int bsw_codec_destroy(bsw_codec *c) {
     cudaFree(c->given); cudaFree(c->mu); cudaFree(c->scale);
     cudaFree(c->sym[0]); cudaFree(c->sym[1]); cudaFree(c->xsym);
     for (auto p : c->zs) cudaFree(p);
-    cudaFree(c->priorP); cudaFree(c->priorC); cudaFree(c->scratch);
+    cudaFree(c->priorP); cudaFree(c->priorC); cudaFree(c->scratch); cudaFree(c->priorCoarse); cudaFree(c->priorFix);
     if (c->st_hi) cudaStreamDestroy(c->st_hi);
     if (c->st_lo) cudaStreamDestroy(c->st_lo);
     for (auto &e : c->ev) cudaEventDestroy(e);
@@ -271,7 +281,9 @@ struct Ctx {
         coder_stream();
         ++nl;
         c->prof.begin(CAT_PRIOR, st);
-        int rc = bsw_ans_pop_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
+        int rc = c->priorCoarse
+            ? bsw_pop_shared_table(s, first, count, c->priorP, c->priorCoarse, c->priorFix, sym, c->zdim, c->S, 31, st)
+            : bsw_ans_pop_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
         c->prof.end(st);
         return rc;
     }
