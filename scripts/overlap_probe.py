@@ -13,7 +13,7 @@ zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
 bins = Bins(cfg, zend, zcen)
 x = torch.from_numpy(synthetic.synthetic_images(cfg, B, seed=7)).cuda()
 w, head = synthetic.initial_words(4096, seed=100)
-for lanes, dual in [(3, 0), (4, 0), (5, 0), (6, 0), (8, 0)]:
+for lanes, dual in [(4, 0), (6, 0), (8, 0)]:
     ss = StreamSet(B, 6144); ss.fill(w, head)
     pc = PipelinedCodec(cfg, sd, bins, B, lanes=lanes)
     pc.set_dual_stream(bool(dual))
