@@ -60,6 +60,20 @@ struct WarpStream2 {          // same state handling as ans_kernels.cu's WarpStr
         uint64_t qd = x / p;
         x = (qd << bits) + (x - qd * p) + c;
     }
+    // same recurrence with the division replaced by a multiply with M = floor((2^64-1)/p) computed in the parallel phase:
+    // floor(x*M / 2^64) is floor(x/p) or one less, so a single correction makes it exact
+    __device__ __forceinline__ void encode_magic(uint32_t p, uint32_t c, uint64_t M, int bits, int lane) {
+        uint64_t lim = ((((uint64_t)1 << 32) >> bits) << 32) * (uint64_t)p;
+        if (x >= lim) {
+            if (len >= cap) { err = BSW_E_OVERFLOW; return; }
+            push_word((uint32_t)x, lane);
+            x >>= 32;
+        }
+        uint64_t qd = __umul64hi(x, M);
+        uint64_t rm = x - qd * p;
+        if (rm >= p) { rm -= p; ++qd; }
+        x = (qd << bits) + rm + c;
+    }
     __device__ __forceinline__ void decode(uint32_t p, uint32_t c, uint32_t m, int bits, int lane) {   // :63-65
         x = (uint64_t)p * (x >> bits) + m - c;
         if (x < ((uint64_t)1 << 32)) {
@@ -109,7 +123,7 @@ __device__ __forceinline__ bool mbar_try_wait_r(uint64_t *bar, uint32_t parity) 
 template <int NB, bool POP, bool USE_TMA>
 __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
-        const int16_t *__restrict__ sym, int bits, int q, uint2 *__restrict__ pairs, uint32_t *__restrict__ coarse,
+        const int16_t *__restrict__ sym, int bits, int q, uint4 *__restrict__ pairs, uint32_t *__restrict__ coarse,
         uint2 *__restrict__ fix, uint32_t *__restrict__ pfull) {
     constexpr int S = 32 * NB;
     using RT = RowTile<NB, USE_TMA>;
@@ -218,13 +232,17 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     } else {
         const uint32_t cb = __shfl_sync(FULL, incl - lsum + pre, owner);      // integer cdf at the symbol, before the remnant
         const uint32_t pb = __shfl_sync(FULL, pv, owner);
-        if (lane == 0) pairs[out] = make_uint2(pb + (bi == sy ? rem : 0u), cb + (bi < sy ? rem : 0u));
+        if (lane == 0) {
+            const uint32_t pf = pb + (bi == sy ? rem : 0u);
+            const uint64_t M = pf == 1u ? ~0ull : ~0ull / (uint64_t)pf;      // reciprocal for the serial phase's division
+            pairs[out] = make_uint4(pf, cb + (bi < sy ? rem : 0u), (uint32_t)M, (uint32_t)(M >> 32));
+        }
     }
 }
 
 // ---- phase B: push -------------------------------------------------------------------------------------------------
 constexpr int BW = 4;
-__global__ void __launch_bounds__(BW * 32) k_push_pairs(bsw_streams sv, int first, int count, const uint2 *__restrict__ pairs,
+__global__ void __launch_bounds__(BW * 32) k_push_pairs(bsw_streams sv, int first, int count, const uint4 *__restrict__ pairs,
                                                         int64_t L, int bits) {
     const int lane = threadIdx.x & 31;
     const int si = blockIdx.x * BW + (threadIdx.x >> 5);
@@ -234,15 +252,17 @@ __global__ void __launch_bounds__(BW * 32) k_push_pairs(bsw_streams sv, int firs
     ws.open(sv, b);
     if (ws.err) return;
     ws.push_begin(lane);
-    const uint2 *pp = pairs + (int64_t)si * L;
-    uint2 nxt = (lane < L) ? __ldg(pp + lane) : make_uint2(1, 0);
+    const uint4 *pp = pairs + (int64_t)si * L;
+    uint4 nxt = (lane < L) ? __ldg(pp + lane) : make_uint4(1, 0, 0xffffffffu, 0xffffffffu);
     for (int64_t i0 = 0; i0 < L && !ws.err; i0 += 32) {
-        uint2 cur = nxt;
+        uint4 cur = nxt;
         int64_t r = i0 + 32 + lane;
         if (r < L) nxt = __ldg(pp + r);                   // prefetch the next 32 rows
         int n = (int)min((int64_t)32, L - i0);
-        for (int j = 0; j < n && !ws.err; ++j)
-            ws.encode(__shfl_sync(FULL, cur.x, j), __shfl_sync(FULL, cur.y, j), bits, lane);
+        for (int j = 0; j < n && !ws.err; ++j) {
+            uint64_t M = ((uint64_t)__shfl_sync(FULL, cur.w, j) << 32) | __shfl_sync(FULL, cur.z, j);
+            ws.encode_magic(__shfl_sync(FULL, cur.x, j), __shfl_sync(FULL, cur.y, j), M, bits, lane);
+        }
     }
     ws.push_end(lane);
     ws.close(sv, b, lane);
@@ -405,7 +425,7 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
     // pop scratch layout: [full table: count*L*S u32 (only if it fits)] [coarse: count*L*NB u32] [fix: count*L uint2]
     const size_t full_bytes = (size_t)count * L * S * 4, small_bytes = (size_t)count * L * NB * 4 + (size_t)count * L * 8;
     const bool full = pop && NB >= 4 && scratch_bytes >= full_bytes + small_bytes;
-    uint2 *pairs = (uint2 *)scratch;
+    uint4 *pairs = (uint4 *)scratch;
     uint32_t *pfull = full ? (uint32_t *)scratch : nullptr;
     uint32_t *coarse = (uint32_t *)((uint8_t *)scratch + (full ? full_bytes : 0));
     uint2 *fix = (uint2 *)((uint8_t *)coarse + (size_t)count * L * NB * 4);
@@ -469,7 +489,7 @@ int bsw_pop_shared_table(bsw_streams *s, int first, int count, const uint32_t *P
 // integer pmf table, which lets the serial pop phase skip its float64 recomputation (used when it fits the budget).
 size_t bsw_rows_scratch_bytes(int count, int64_t L, int S, bool full) {
     size_t small = (size_t)count * L * (S / 32) * 4 + (size_t)count * L * 8;
-    size_t push = (size_t)count * L * 8;
+    size_t push = (size_t)count * L * 16;
     size_t pop = small + (full ? (size_t)count * L * S * 4 : 0);
     return pop > push ? pop : push;
 }
