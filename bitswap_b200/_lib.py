@@ -74,6 +74,8 @@ def lib():
         L = ctypes.CDLL(SO_PATH)
         L.bsw_last_error.restype = ctypes.c_char_p
         L.bsw_streams_capacity.restype = ctypes.c_int64
+        if hasattr(L, "bsw_logistic_scratch_bytes"):
+            L.bsw_logistic_scratch_bytes.restype = ctypes.c_int64
         if hasattr(L, "bsw_codec_last_launches"):
             L.bsw_codec_last_launches.restype = ctypes.c_int64
         _set_argtypes(L)
@@ -105,6 +107,9 @@ def _set_argtypes(L):
         "bsw_logistic_tables": [P, L64, P, P, L64, L64, I, I, I, P, P, P],
         "bsw_logistic_push": [P, I, I, P, L64, P, L64, P, L64, P, L64, I, I, I, P],
         "bsw_logistic_pop": [P, I, I, P, L64, P, L64, P, L64, P, L64, I, I, I, P],
+        "bsw_logistic_scratch_bytes": [I, L64, I, I],
+        "bsw_logistic_push_2p": [P, I, I, P, L64, P, L64, P, L64, P, L64, I, I, I, P, L64, P],
+        "bsw_logistic_pop_2p": [P, I, I, P, L64, P, L64, P, L64, P, L64, I, I, I, P, L64, P],
         "bsw_bins_create": [PP, I, I, I, I, P, P],
         "bsw_bins_destroy": [P],
         "bsw_bins_device_ptrs": [P, I, PP, PP, PP],
@@ -136,7 +141,8 @@ def _set_argtypes(L):
 EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure_fp64_peak", "bsw_selftest_cdf", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
            "bsw_streams_capacity", "bsw_streams_import", "bsw_streams_fill", "bsw_streams_sizes", "bsw_streams_min_words", "bsw_streams_export",
            "bsw_streams_device_ptrs", "bsw_streams_pack", "bsw_streams_unpack", "bsw_streams_total_words", "bsw_ans_tables", "bsw_ans_push", "bsw_ans_pop",
-           "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_bins_create",
+           "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_logistic_scratch_bytes", "bsw_logistic_push_2p",
+           "bsw_logistic_pop_2p", "bsw_bins_create",
            "bsw_bins_destroy", "bsw_bins_device_ptrs", "bsw_gather_zcentres", "bsw_gather_xcentres",
            "bsw_model_create", "bsw_model_destroy", "bsw_model_load_conv", "bsw_model_load_gen_std",
            "bsw_model_finalize", "bsw_vae_infer", "bsw_vae_generate", "bsw_codec_create", "bsw_codec_destroy",

@@ -593,3 +593,26 @@ extern "C" int bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_ho
     *mismatches_host = (int64_t)h;
     return BSW_OK;
 }
+
+// ---- C ABI of the two-phase coder (same contract as bsw_logistic_push/pop + caller-provided scratch) -----------------
+extern "C" int64_t bsw_logistic_scratch_bytes(int count, int64_t L, int S, int full_tables) {
+    return (int64_t)bsw_rows_scratch_bytes(count, L, S, full_tables != 0);
+}
+extern "C" int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc, int64_t sss,
+                                    const double *endp, int64_t ers, const int16_t *sym, int64_t L, int S, int bits, int q,
+                                    void *scratch, int64_t scratch_bytes, void *stream) {
+    int rc = bsw_logistic_2p(0, false, s, first, count, mu, mss, sc, sss, endp, ers, (int16_t *)sym, L, S, bits, q, scratch,
+                             (size_t)scratch_bytes, (cudaStream_t)stream);
+    if (rc) return rc;
+    return bsw_logistic_2p(1, false, s, first, count, mu, mss, sc, sss, endp, ers, (int16_t *)sym, L, S, bits, q, scratch,
+                           (size_t)scratch_bytes, (cudaStream_t)stream);
+}
+extern "C" int bsw_logistic_pop_2p(bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc, int64_t sss,
+                                   const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
+                                   void *scratch, int64_t scratch_bytes, void *stream) {
+    int rc = bsw_logistic_2p(0, true, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, S, bits, q, scratch,
+                             (size_t)scratch_bytes, (cudaStream_t)stream);
+    if (rc) return rc;
+    return bsw_logistic_2p(1, true, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, S, bits, q, scratch,
+                           (size_t)scratch_bytes, (cudaStream_t)stream);
+}

@@ -146,6 +146,20 @@ int bsw_logistic_pop(bsw_streams *s, int first, int count, const float *mu_dev, 
                      int64_t endp_row_stride, int16_t *sym_dev, int64_t L, int S, int bits,
                      int quantbits, void *stream);
 
+/* Two-phase variants (the throughput path of the codec): a fully parallel float64 row-table kernel followed by the
+ * serial integer coder; same arguments and bit-identical results, plus caller-provided device scratch of at least
+ * bsw_logistic_scratch_bytes(count, L, S, 0) bytes.  With bsw_logistic_scratch_bytes(count, L, S, 1) bytes the pop
+ * keeps the whole integer table of the level and its serial phase needs no float64 work (small batches). */
+int64_t bsw_logistic_scratch_bytes(int count, int64_t L, int S, int full_tables);
+int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
+                         const float *scale_dev, int64_t scale_stream_stride, const double *endpoints_dev,
+                         int64_t endp_row_stride, const int16_t *sym_dev, int64_t L, int S, int bits, int quantbits,
+                         void *scratch_dev, int64_t scratch_bytes, void *stream);
+int bsw_logistic_pop_2p(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
+                        const float *scale_dev, int64_t scale_stream_stride, const double *endpoints_dev,
+                        int64_t endp_row_stride, int16_t *sym_dev, int64_t L, int S, int bits, int quantbits,
+                        void *scratch_dev, int64_t scratch_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Bin tables on the device.
  * Replaces: the tensors returned by discretize() (discretization.py:9-99) and ImageBins

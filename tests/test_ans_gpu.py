@@ -306,3 +306,71 @@ def test_packed_export_import_roundtrip():
     assert ss2.export_lists() == states
     sub_w, sub_o, sub_h = ss.export_packed(first=5, count=9)
     assert np.array_equal(sub_o, o[5:15] - o[5]) and np.array_equal(sub_w, w[o[5]:o[14]])
+
+
+def _pad_big(ends):
+    L, Sm1 = ends.shape
+    out = np.full((L, Sm1 + 1), 1e300)
+    out[:, :Sm1] = ends
+    return out
+
+
+@pytest.mark.parametrize("S,q,full", [(1024, 10, 0), (1024, 10, 1), (256, 8, 1), (128, 7, 0), (64, 6, 0), (32, 5, 0)])
+def test_two_phase_abi_extreme_tables_vs_fused_and_oracle(S, q, full):
+    """Two-phase coder through the C ABI against the fused kernels and the oracle (fed our exact pmfs), on hostile rows:
+    sigma at the x-level minimum (2/255/8) so that almost every bin is a saturated tail (P = 1, huge remnant), means far
+    outside the bin range, symbols in the dead tails, plus ordinary rows."""
+    rs = np.random.RandomState(S + full)
+    B, L = 9, 96
+    lo, hi = -6 - rs.uniform(0, 1, L), 6 + rs.uniform(0, 1, L)
+    ends = np.linspace(lo, hi, S + 1, axis=1)[:, 1:-1].copy()
+    mu = rs.normal(0, 2, (B, L)).astype(np.float32)
+    sc = rs.uniform(0.1, 1.0, (B, L)).astype(np.float32)
+    sc[:, 0::4] = np.float32((2. / 255.) / 8.)                 # needle-sharp rows
+    mu[:, 1::8] = rs.choice([-25.0, 25.0, -7.5, 7.5], size=mu[:, 1::8].shape).astype(np.float32)    # mass outside the bins
+    e_pad = torch.from_numpy(_pad_big(ends)).to(dev)
+    e_raw = torch.from_numpy(ends).to(dev)
+    dmu, dsc = torch.from_numpy(mu).to(dev), torch.from_numpy(sc).to(dev)
+    nbytes = int(lib().bsw_logistic_scratch_bytes(B, L, S, full))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(3000 + b, seed=500 + b)
+        states.append([int(v) for v in w] + [head])
+    tabs = []
+    for b in range(B):
+        pm = torch.empty((L, S), dtype=torch.float64, device=dev)
+        m64, s64 = dmu[b].double().contiguous(), dsc[b].double().contiguous()
+        check(lib().bsw_logistic_pmfs(e_raw.data_ptr(), S - 1, m64.data_ptr(), s64.data_ptr(), 1, L, S, pm.data_ptr(), cuda_stream_ptr()))
+        torch.cuda.synchronize()
+        tabs.append(O.tables_c(pm.cpu().numpy(), 31, q))
+    sym = rs.randint(0, S, size=(B, L)).astype(np.int16)
+    sym[:, :6] = [0, S - 1, 1, S - 2, S // 2, 0]
+    dsym = torch.from_numpy(sym).to(dev)
+    res = {}
+    for name in ("2p", "fused"):
+        ss = StreamSet(B, 1 << 14)
+        ss.import_lists(states)
+        out = torch.zeros((B, L), dtype=torch.int16, device=dev)
+        if name == "2p":
+            check(lib().bsw_logistic_pop_2p(ss.handle, 0, B, dmu.data_ptr(), L, dsc.data_ptr(), L, e_pad.data_ptr(), S, out.data_ptr(),
+                                            L, S, 31, q, scratch.data_ptr(), nbytes, cuda_stream_ptr()))
+        else:
+            check(lib().bsw_logistic_pop(ss.handle, 0, B, dmu.data_ptr(), L, dsc.data_ptr(), L, e_pad.data_ptr(), S, out.data_ptr(),
+                                         L, S, 31, q, cuda_stream_ptr()))
+        ss.raise_on_error()
+        after_pop, popped = ss.export_lists(), out.cpu().numpy().copy()
+        if name == "2p":
+            check(lib().bsw_logistic_push_2p(ss.handle, 0, B, dmu.data_ptr(), L, dsc.data_ptr(), L, e_pad.data_ptr(), S, dsym.data_ptr(),
+                                             L, S, 31, q, scratch.data_ptr(), nbytes, cuda_stream_ptr()))
+        else:
+            check(lib().bsw_logistic_push(ss.handle, 0, B, dmu.data_ptr(), L, dsc.data_ptr(), L, e_pad.data_ptr(), S, dsym.data_ptr(),
+                                          L, S, 31, q, cuda_stream_ptr()))
+        ss.raise_on_error()
+        res[name] = (after_pop, popped, ss.export_lists())
+    assert res["2p"][0] == res["fused"][0] and np.array_equal(res["2p"][1], res["fused"][1]) and res["2p"][2] == res["fused"][2]
+    for b in range(B):
+        a = O.AnsC(tables=tabs[b])
+        st, s_ = a.decode(O.CState.from_list(states[b]))
+        assert np.array_equal(res["2p"][1][b], s_) and res["2p"][0][b] == st.to_list()
+        assert res["2p"][2][b] == a.encode(st, sym[b].astype(np.int64)).to_list()
