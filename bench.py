@@ -364,7 +364,7 @@ def main():
 
     # ---- roofline for the dominant kernel category ---------------------------------------------------------
     fl, ab, sg = conv_flops(cfg), ans_bytes(cfg), sigmoids(cfg)
-    FP64_PER_SIGMOID = 27        # FP64-pipe instructions per cdf value in k_rows' SASS (DESIGN.md "ANS kernels")
+    FP64_PER_SIGMOID = 16        # FP64-pipe instructions per cdf value in the screened k_rows loop (DESIGN.md "ANS kernels")
     fp64_peak = _lib.measure_fp64_peak()                                     # DFMA lanes/s, measured on this GPU
     Bl = B                                                       # images per profiled kernel launch
     nsig_z, nsig_x = cfg.zdim * (cfg.zsupport - 1) * Bl, cfg.xdim * 255 * Bl

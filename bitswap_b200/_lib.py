@@ -131,6 +131,7 @@ def _set_argtypes(L):
         "bsw_codec_set_two_phase": [P, I],
         "bsw_codec_set_dual_stream": [P, I],
         "bsw_selftest_cdf": [L64, U64, P, P],
+        "bsw_selftest_cdf_apx": [L64, U64, P],
     }
     for name, args in sig.items():
         fn = getattr(L, name, None)
@@ -138,7 +139,7 @@ def _set_argtypes(L):
             fn.argtypes = args
 
 
-EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure_fp64_peak", "bsw_selftest_cdf", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
+EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure_fp64_peak", "bsw_selftest_cdf", "bsw_selftest_cdf_apx", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
            "bsw_streams_capacity", "bsw_streams_import", "bsw_streams_fill", "bsw_streams_sizes", "bsw_streams_min_words", "bsw_streams_export",
            "bsw_streams_device_ptrs", "bsw_streams_pack", "bsw_streams_unpack", "bsw_streams_total_words", "bsw_ans_tables", "bsw_ans_push", "bsw_ans_pop",
            "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_logistic_scratch_bytes", "bsw_logistic_push_2p",

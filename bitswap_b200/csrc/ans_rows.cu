@@ -16,6 +16,8 @@
 //
 // Results are bit-identical to the fused kernels (integer sums are associative; the cdf function is shared).
 #include <stdlib.h>
+#include <type_traits>
+#include <string.h>
 #include "bsw_common.cuh"
 
 #define FULL 0xffffffffu
@@ -120,7 +122,22 @@ __device__ __forceinline__ bool mbar_try_wait_r(uint64_t *bar, uint32_t parity) 
     return ok != 0;
 }
 
-template <int NB, bool POP, bool USE_TMA>
+// exact integer pmf (before the +1) of bin j of this lane's block: the rare path of the screened kernel
+template <int NB, int STRIDE>
+__device__ __noinline__ uint32_t rows_exact_pm(const double *tile, int lane, int j, double m, double s, double rs, double mult) {
+    const double c = bsw_cdf_fast(tile[lane * STRIDE + j], m, s, rs);
+    double p = 0.0;                                       // lower edge of bin 0 is cdf = 0 (cifar_compress.py:184)
+    if (j > 0) p = bsw_cdf_fast(tile[lane * STRIDE + j - 1], m, s, rs);
+    else if (lane > 0) p = bsw_cdf_fast(tile[(lane - 1) * STRIDE + NB - 1], m, s, rs);
+    return __double2uint_rz(__dmul_rn(__dsub_rn(c, p), mult));
+}
+
+// APX = true (default): every cdf value comes from the 15-instruction screening function bsw_cdf_apx; the pmf is formed
+// in 2^-20 fixed point with one FMA against a 2^52-type magic constant, and any bin whose scaled pmf lands within
+// BSW_APX_WINDOW of an integer boundary (about 1.2e-4 of them) is recomputed with the exact bsw_cdf_fast.  The integers
+// this kernel emits are therefore those of the exact function, which is what k_pop_coarse re-evaluates and what the
+// fused kernels produce.  APX = false (BSW_ROWS_EXACT=1) evaluates the exact function for every bin.
+template <int NB, bool POP, bool USE_TMA, bool APX>
 __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint4 *__restrict__ pairs, uint32_t *__restrict__ coarse,
@@ -128,11 +145,13 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     constexpr int S = 32 * NB;
     using RT = RowTile<NB, USE_TMA>;
     __shared__ __align__(16) double tile[RT::DOUBLES];
+    __shared__ __align__(16) double t32[APX ? BSW_APX_TABLE_DOUBLES : 2];
     __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = blockIdx.x;                      // row index i within the level
     const int si = blockIdx.y * RW + warp;               // stream
     const double *e = endp + row * ers;
+    if (APX) bsw_apx_table_fill(t32, threadIdx.x, RW * 32);
     if (RT::TMA) {
         // TMA-staged endpoint tile: 32 bulk copies (one per lane-chunk, NB*8 bytes each) complete on one mbarrier
         if (threadIdx.x == 0) {
@@ -157,63 +176,112 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];
     const double rs = __ddiv_rn(1.0, s);
     const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));
+    const double mult2 = mult * 1048576.0;               // pmf in 2^-20 fixed point: < 2^51 for bits <= 31
+    const double magic2 = 6755399441055744.0 + (double)BSW_APX_WINDOW;
     int sy = 0;
     if (!POP) sy = (int)sym[(int64_t)si * L + row];
     const int owner = sy / NB, js = sy - owner * NB;     // push: lane and in-lane position of the coded symbol
 
     BswExpRegs K;
-    K.load();
+    BswApxRegs KA;
+    if (APX) KA.load(); else K.load();
     const double *my = tile + lane * RT::STRIDE;
+    const uint32_t tl = smem_u32r(t32) + 8u * lane;
+    // The screening cdf needs |t| <= 690 (its exponent arithmetic has no range checks).  Rows are sorted, so if both ends
+    // of the row are inside that range for this stream's (mu, sigma) every bin is, and the three clamp instructions per
+    // value are skipped (warp-uniform: a warp is one stream).  Needle-sharp x rows take the clamped loop.
+    bool wide = true;
+    if (APX && S > 2) {
+        const double t_lo = __dmul_rn(__dsub_rn(tile[0], m), rs);
+        const double t_hi = __dmul_rn(__dsub_rn(tile[((S - 2) / NB) * RT::STRIDE + ((S - 2) % NB)], m), rs);
+        wide = !(fabs(t_lo) <= 690.0 && fabs(t_hi) <= 690.0);
+    }
+    auto cdf_at = [&](int j, auto clampc) -> double {
+        if (APX) return bsw_cdf_apx<decltype(clampc)::value>(my[j], m, rs, tl, KA);
+        return bsw_cdf_fast_regs(my[j], m, s, rs, K);
+    };
     // cdf at my last endpoint first: the next lane needs it as the lower neighbour of its first bin.  The row's very
     // last entry is the +1e300 pad: t clamps to +690 and the cdf comes out as exactly 1.0, the reference's
     // `1. - cdfs[:,-1]` upper bound of the last bin (cifar_compress.py:184).
-    const double c_last = bsw_cdf_fast_regs(my[NB - 1], m, s, rs, K);
+    const double c_last = cdf_at(NB - 1, std::true_type{});
     const double up = __shfl_up_sync(FULL, c_last, 1);
     double prev = lane == 0 ? 0.0 : up;
-    uint32_t lsum = 0, lbest = 0, pre = 0, pv = 0;
-    int lbi = 0;
     // pop, small batches: also keep every integer pmf of the row (before the remnant) so that the serial phase needs no
     // float64 work at all (k_pop_full); written as one 16-byte store per 4 bins
     constexpr int G = NB >= 4 ? 4 : NB;                  // bins per group
     uint32_t *prow = (POP && pfull) ? pfull + ((int64_t)si * L + row) * S + lane * NB : nullptr;
-    auto account = [&](uint32_t v, int j) {
-        lsum += v;
-        if (v > lbest) { lbest = v; lbi = j; }
-        if (!POP) {
-            pre += (j < js) ? v : 0u;
-            if (j == js) pv = v;
-        }
-    };
-#pragma unroll 1
-    for (int j0 = 0; j0 < NB - G; j0 += G) {
+    // running state of my block: sum, the group holding the (first) maximum, and for push the integer cdf below the symbol
+    uint32_t lsum = 0, lbest = 0, pre = 0, pv = 0;
+    uint32_t bestv[G];
+    int bestj0 = 0;
+#pragma unroll
+    for (int t = 0; t < G; ++t) bestv[t] = 0;
+    auto group = [&](int j0, auto last_group, auto clampc) {
         uint32_t vv[G];
+        bool doubt[G];
+        bool any = false;
+        uint32_t all_hi = 0x80000000u;
 #pragma unroll
         for (int t = 0; t < G; ++t) {
-            const double c = bsw_cdf_fast_regs(my[j0 + t], m, s, rs, K);
-            vv[t] = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;            // :29 trunc, :32 +1
+            const double c = (decltype(last_group)::value && t == G - 1) ? c_last : cdf_at(j0 + t, clampc);
+            if (APX) {
+                // z = 1.5*2^52 + WINDOW + pmf*2^20: the mantissa of z holds the fixed-point pmf, shifted by WINDOW so that
+                // "low 20 bits < 2*WINDOW" means "within WINDOW of a truncation boundary".  The funnel shift drops the low
+                // 20 bits; what remains is the integer pmf with the 2^51 magic bit on top (bit 31).
+                const double z = __fma_rn(__dsub_rn(c, prev), mult2, magic2);
+                const uint32_t raw = __funnelshift_r((uint32_t)__double2loint(z), (uint32_t)__double2hiint(z), 20);
+                // a pmf that truncates to 0 needs no second look: the exact value then lies in (-1, 1) as well
+                doubt[t] = ((uint32_t)__double2loint(z) & (0xfffffu & ~(2u * BSW_APX_WINDOW - 1u))) == 0u && raw != 0x80000000u;
+                any |= doubt[t];
+                all_hi &= raw;                            // bit 31 clear = negative pmf (unsorted endpoints): exact path
+                vv[t] = raw + 0x80000001u;                                                 // :29 trunc, :32 +1
+            } else {
+                vv[t] = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;
+            }
             prev = c;
-            account(vv[t], j0 + t);
+        }
+        if (APX && (any || !(all_hi & 0x80000000u))) {
+            const bool all = !(all_hi & 0x80000000u);
+#pragma unroll
+            for (int t = 0; t < G; ++t)
+                if (doubt[t] || all) vv[t] = rows_exact_pm<NB, RT::STRIDE>(tile, lane, j0 + t, m, s, rs, mult) + 1u;
+        }
+        uint32_t gsum = 0, gmax = 0;
+#pragma unroll
+        for (int t = 0; t < G; ++t) { gsum += vv[t]; gmax = max(gmax, vv[t]); }
+        lsum += gsum;
+        if (gmax > lbest) {                               // strict: the earlier group keeps a tie (:35 first maximum)
+            lbest = gmax; bestj0 = j0;
+#pragma unroll
+            for (int t = 0; t < G; ++t) bestv[t] = vv[t];
+        }
+        if (!POP) {                                       // js is the same in every lane, so these branches are warp-uniform
+            if (j0 + G <= js) pre += gsum;
+            else if (j0 <= js) {
+#pragma unroll
+                for (int t = 0; t < G; ++t) {
+                    pre += (j0 + t < js) ? vv[t] : 0u;
+                    if (j0 + t == js) pv = vv[t];
+                }
+            }
         }
         if (POP && prow) {
             if (G == 4) *reinterpret_cast<uint4 *>(prow + j0) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
             else for (int t = 0; t < G; ++t) prow[j0 + t] = vv[t];
         }
+    };
+    if (wide) {
+#pragma unroll 1
+        for (int j0 = 0; j0 < NB - G; j0 += G) group(j0, std::false_type{}, std::true_type{});
+        group(NB - G, std::true_type{}, std::true_type{});
+    } else {
+#pragma unroll 1
+        for (int j0 = 0; j0 < NB - G; j0 += G) group(j0, std::false_type{}, std::false_type{});
+        group(NB - G, std::true_type{}, std::false_type{});   // its last bin is the lane's last bin, whose cdf is already known
     }
-    {   // last group: its last bin is the lane's last bin, whose cdf is already known
-        uint32_t vv[G];
+    int lbi = bestj0;                                     // first position of the maximum inside its group
 #pragma unroll
-        for (int t = 0; t < G; ++t) {
-            const int j = NB - G + t;
-            const double c = (t == G - 1) ? c_last : bsw_cdf_fast_regs(my[j], m, s, rs, K);
-            vv[t] = __double2uint_rz(__dmul_rn(__dsub_rn(c, prev), mult)) + 1u;
-            prev = c;
-            account(vv[t], j);
-        }
-        if (POP && prow) {
-            if (G == 4) *reinterpret_cast<uint4 *>(prow + NB - G) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-            else for (int t = 0; t < G; ++t) prow[NB - G + t] = vv[t];
-        }
-    }
+    for (int t = G - 1; t >= 0; --t) if (bestv[t] == lbest) lbi = bestj0 + t;
     uint32_t incl = lsum;
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(FULL, incl, o);
@@ -434,13 +502,17 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
     // 256-byte bulk copies are too small to beat two in-flight loads per thread, so TMA staging is the documented option,
     // not the default.
     static const bool tma = getenv("BSW_ROWS_TMA") && getenv("BSW_ROWS_TMA")[0] == '1';
+    // BSW_ROWS_EXACT=1: evaluate the exact cdf for every bin instead of screening with bsw_cdf_apx (A/B switch; same output)
+    static const bool exact = tma || bits > 31 || (getenv("BSW_ROWS_EXACT") && getenv("BSW_ROWS_EXACT")[0] == '1');
     if (phase == 0) {
         if (pop) {
-            if (tma) k_rows<NB, true, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
-            else k_rows<NB, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
+            if (tma) k_rows<NB, true, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
+            else if (exact) k_rows<NB, true, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
+            else k_rows<NB, true, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
         } else {
-            if (tma) k_rows<NB, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
-            else k_rows<NB, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
+            if (tma) k_rows<NB, false, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
+            else if (exact) k_rows<NB, false, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
+            else k_rows<NB, false, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
         }
     } else {
         if (pop && full) k_pop_full<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, 0);
@@ -575,6 +647,43 @@ __global__ void k_cdf_selftest(int64_t n, uint64_t seed, unsigned long long *bad
         atomicAdd(bad, 1ULL);
         worst[0] = e; worst[1] = mu; worst[2] = sc; worst[3] = a; worst[4] = b;
     }
+}
+// ---- self-test of the screening function: worst |bsw_cdf_apx - bsw_cdf_fast| in units of 2^-51 (what the window is in) ----
+__global__ void k_cdf_apx_selftest(int64_t n, uint64_t seed, unsigned long long *worst_bits) {
+    __shared__ double t32[BSW_APX_TABLE_DOUBLES];
+    bsw_apx_table_fill(t32, threadIdx.x, blockDim.x);
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = seed + (uint64_t)i * 0x9E3779B97F4A7C15ULL;
+    auto nxt = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (double)(x >> 11) * (1.0 / 9007199254740992.0); };
+    nxt();
+    int mode = (int)(i & 7);
+    float scf = (mode < 4) ? (float)(0.1 + 0.9 * nxt()) : (mode < 6 ? (float)(0.00098 + 0.05 * nxt()) : (float)(0.0009 + 2.0 * nxt()));
+    float muf = (float)((nxt() - 0.5) * (mode < 4 ? 14.0 : 2.2));
+    double e = (nxt() - 0.5) * (mode < 4 ? 14.0 : 2.2);
+    if (mode == 3) e = muf + (nxt() - 0.5) * 8.0 * scf;                  // the steep part of the curve
+    if (mode == 7) e = (double)(float)e;
+    double sc = (double)scf, mu = (double)muf, rs = __ddiv_rn(1.0, sc);
+    BswApxRegs KA;
+    KA.load();
+    double a = bsw_cdf_apx<true>(e, mu, rs, smem_u32r(t32) + 8u * (threadIdx.x & 31), KA), b = bsw_cdf_fast(e, mu, sc, rs);
+    double err = fabs(a - b) * 2251799813685248.0;                        // 2^51
+    if (!(err == err)) err = 1e300;
+    atomicMax(worst_bits, (unsigned long long)__double_as_longlong(err));
+}
+extern "C" int bsw_selftest_cdf_apx(int64_t n, uint64_t seed, double *worst_units_host) {
+    BSW_REQUIRE(n > 0 && worst_units_host, "bad arguments");
+    unsigned long long *w = nullptr;
+    BSW_CUDA(cudaMalloc(&w, 8));
+    BSW_CUDA(cudaMemset(w, 0, 8));
+    k_cdf_apx_selftest<<<(unsigned)((n + 255) / 256), 256>>>(n, seed, w);
+    BSW_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    BSW_CUDA(cudaMemcpy(&h, w, 8, cudaMemcpyDeviceToHost));
+    cudaFree(w);
+    memcpy(worst_units_host, &h, 8);
+    return BSW_OK;
 }
 extern "C" int bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_host, double *example_host) {
     BSW_REQUIRE(n > 0 && mismatches_host, "bad arguments");

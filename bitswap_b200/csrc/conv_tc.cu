@@ -39,14 +39,21 @@ constexpr int WTILE_BYTES = BN * BK * 2;    // one 128-row weight tile = 8 KB
 constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * WTILE_BYTES; // A_hi, A_lo, B_hi, B_lo = 48 KB
 constexpr int TC_THREADS = 320;             // 10 warps
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// half-image variant (k_conv_tc_h): M = 128 pixels per CTA, 256 TMEM columns, 3 x 32 KB stages -> two CTAs per SM
+constexpr int H_TILE_BYTES = 128 * BK * 2;  // 8 KB
+constexpr int H_STAGE_BYTES = 2 * H_TILE_BYTES + 2 * WTILE_BYTES;   // 32 KB
+constexpr int H_NSTAGE = 3;
+constexpr int H_SMEM_BYTES = H_NSTAGE * H_STAGE_BYTES + 1024 + 256;
 
 struct TcState {
     // bf16 hi/lo activation planes, ping-pong: [max_batch, 256 px, 256 ch]
     __nv_bfloat16 *act[2][2];
     CUtensorMap act_map[2][2];
+    CUtensorMap act_map_h[2][2];   // same planes, box = 8 image rows (k_conv_tc_h)
     // in-conv input: the flat `given` re-laid as NHWC bf16 hi/lo planes with the (1..12) input channels padded to 32
     __nv_bfloat16 *inp[2];
     CUtensorMap inp_map[2];
+    CUtensorMap inp_map_h[2];
     std::vector<void *> wbufs;
 };
 
@@ -317,6 +324,149 @@ k_conv_tc_c2(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant_
     conv_tc_body<true>(amap_hi, amap_lo, wmap_hi, wmap_lo, a);
 }
 
+// Half-image variant: the default for the in-convs (0.555 -> 0.416 ms per launch at B=1024), optional for the dense convs.
+// k_conv_tc above owns the SM (192 KB of stages, all 512 TMEM columns), so the tensor
+// pipe idles while its eight epilogue warps drain the accumulators to HBM -- about half of a 3x3 launch and nearly all
+// of an in-conv launch (13.8 waves x ~40 us per CTA with nine k-blocks of work).  Here a CTA owns 128 pixels (8 image
+// rows) x 128 output channels: {main, cross} x 128 columns = 256 TMEM columns and 3 x 32 KB stages, so TWO CTAs are
+// resident per SM and one's epilogue runs under the other's MMAs.  Price: the weight tile is fetched per half image
+// (L2->SM bytes per k-block and MMA row 48 KB/256 rows -> 32 KB/128 rows); the order of the k-blocks and of the MMAs
+// into each accumulator is unchanged, so results are bit-identical to the full-tile kernel.
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_conv_tc_h(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
+            const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = (uint64_t *)(smem + H_NSTAGE * H_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + H_NSTAGE;
+    uint64_t *acc_bar = empty_bar + H_NSTAGE;
+    uint32_t *tmem_ptr = (uint32_t *)(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img = blockIdx.x, co0 = blockIdx.y * BN, mh = blockIdx.z;
+    const int nkb = a.taps * a.cchunks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_lo) : "memory");
+        for (int s = 0; s < H_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {     // TMEM: 256 columns = main [0,128) + cross [128,256); the co-resident CTA takes the other 256
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {     // ===== TMA producer =====
+            const int r = a.ks / 2;
+            int stage = 0, phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                int tap = kb / a.cchunks, c0 = (kb - tap * a.cchunks) * BK;
+                int dy = tap / a.ks, dx = tap - dy * a.ks;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t *st = smem + stage * H_STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], H_STAGE_BYTES);
+                tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r + 8 * mh, img);
+                tma_load_4d(st + H_TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r + 8 * mh, img);
+                tma_load_3d(st + 2 * H_TILE_BYTES, &wmap_hi, &full_bar[stage], c0, co0, tap);
+                tma_load_3d(st + 2 * H_TILE_BYTES + WTILE_BYTES, &wmap_lo, &full_bar[stage], c0, co0, tap);
+                if (++stage == H_NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {     // ===== MMA issuer =====
+            int stage = 0, phase = 0;
+            const uint32_t d_main = tmem_base, d_cross = tmem_base + BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                uint32_t sbase = smem_u32(smem + stage * H_STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                    uint64_t a_hi = make_desc_sw64(sbase + kk * 32);
+                    uint64_t a_lo = make_desc_sw64(sbase + H_TILE_BYTES + kk * 32);
+                    uint64_t b_hi = make_desc_sw64(sbase + 2 * H_TILE_BYTES + kk * 32);
+                    uint64_t b_lo = make_desc_sw64(sbase + 2 * H_TILE_BYTES + WTILE_BYTES + kk * 32);
+                    umma_bf16(d_main, a_hi, b_hi, (kb | kk) != 0);
+                    umma_bf16(d_cross, a_lo, b_hi, (kb | kk) != 0);
+                    umma_bf16(d_cross, a_hi, b_lo, 1);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == H_NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_bar);
+        }
+    } else {
+        // ===== epilogue: warp w may read TMEM lanes 32*(w%4)..; the two warps of a quadrant split the 128 columns =====
+        const int ew = warp - 2;
+        const int chalf = ew >> 2;
+        const int quad = warp & 3;
+        const int p = mh * 128 + quad * 32 + lane;       // pixel
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        const int64_t row = ((int64_t)img * 256 + p) * 256;
+#pragma unroll 1
+        for (int cc = chalf * 64; cc < chalf * 64 + 64; cc += 32) {
+            const int c0 = co0 + cc;
+            uint32_t rr[32], rc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc, rr);
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + BN + cc, rc);
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (__uint_as_float(rr[i]) + __uint_as_float(rc[i])) + __ldg(a.bias + c0 + i);
+            if (a.resid) {
+                const float4 *rp = reinterpret_cast<const float4 *>(a.resid + row + c0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 q = rp[i];
+                    v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+                }
+            }
+            if (a.T_elu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = elu1(v[i]);
+            }
+            if (a.T) {
+                float4 *tp = reinterpret_cast<float4 *>(a.T + row + c0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (a.A_hi) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float x0 = a.A_elu ? elu1(v[2 * i]) : v[2 * i], x1 = a.A_elu ? elu1(v[2 * i + 1]) : v[2 * i + 1];
+                    __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                    __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                uint4 *hp = reinterpret_cast<uint4 *>(a.A_hi + row + c0), *lp = reinterpret_cast<uint4 *>(a.A_lo + row + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    hp[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                    lp[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // float32 NHWC -> bf16 hi/lo planes (used once per net, after the SIMT in-conv)
 __global__ void k_split_planes(const float *__restrict__ in, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,6 +545,8 @@ int bsw_model_tc_prepare(bsw_model *m) {
             cuuint64_t str[3] = {256 * 2, 16 * 256 * 2, 256 * 256 * 2};
             cuuint32_t box[4] = {BK, 16, 16, 1};
             if (int rc = encode_map(&ts->act_map[b][pl], ts->act[b][pl], 4, dims, str, box)) return rc;
+            cuuint32_t boxh[4] = {BK, 16, 8, 1};
+            if (int rc = encode_map(&ts->act_map_h[b][pl], ts->act[b][pl], 4, dims, str, boxh)) return rc;
         }
     for (int pl = 0; pl < 2; ++pl) {
         size_t elems = (size_t)m->d.max_batch * 256 * 32;
@@ -403,6 +555,8 @@ int bsw_model_tc_prepare(bsw_model *m) {
         cuuint64_t str[3] = {32 * 2, 16 * 32 * 2, 256 * 32 * 2};
         cuuint32_t box[4] = {BK, 16, 16, 1};
         if (int rc = encode_map(&ts->inp_map[pl], ts->inp[pl], 4, dims, str, box)) return rc;
+        cuuint32_t boxh[4] = {BK, 16, 8, 1};
+        if (int rc = encode_map(&ts->inp_map_h[pl], ts->inp[pl], 4, dims, str, boxh)) return rc;
     }
     // weights: [tap][o=256][c=Kc] bf16 hi/lo planes, K (=c) innermost; Kc = 256 for the dense convs, 32 for the in-convs
     std::vector<TcSlot> *slots = new std::vector<TcSlot>();
@@ -445,6 +599,7 @@ int bsw_model_tc_prepare(bsw_model *m) {
     m->tc_slots = slots;
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     m->tc_ready = true;
     return BSW_OK;
 }
@@ -493,7 +648,14 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     // B=1024): the kernel issues 1.03-1.32 PFLOP/s of MMAs, i.e. it sits at the measured sustained bf16 rate, not at the
     // L2->SM limit the multicast relieves.  It stays selectable (BSW_TC_CLUSTER=1) as the documented experiment.
     static const bool use_cluster = getenv("BSW_TC_CLUSTER") && getenv("BSW_TC_CLUSTER")[0] == '1';
-    if (use_cluster)
+    // Dense convs: the half-image kernel measured 0.856 (3x3) / 2.058 ms (5x5) against 0.875 / 1.896 ms for the full tile at
+    // B=1024 -- the MMAs already run at the sustained bf16 rate, so hiding the epilogue buys nothing and the re-fetched
+    // weight tiles cost the 5x5.  Full tile stays the default here; BSW_TC_HALFTILE=1 selects the other one.
+    static const bool half_tile = getenv("BSW_TC_HALFTILE") && getenv("BSW_TC_HALFTILE")[0] == '1';
+    if (!use_cluster && half_tile)
+        k_conv_tc_h<<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
+                                                                                   s.map_hi, s.map_lo, t);
+    else if (use_cluster)
         k_conv_tc_c2<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
                                                                               s.map_hi, s.map_lo, t);
     else
@@ -519,7 +681,9 @@ int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n
     t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
-    k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
+    static const bool full_tile = getenv("BSW_TC_FULLTILE") && getenv("BSW_TC_FULLTILE")[0] == '1';
+    if (full_tile) k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
+    else k_conv_tc_h<<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t);
     BSW_LAUNCH_CHECK();
     *launches += 2;
     return BSW_OK;

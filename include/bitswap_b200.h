@@ -44,6 +44,8 @@ int         bsw_measure_fp64_peak(double *dfma_per_s);
 /* Device self-test: the lean cdf of the throughput kernels vs the exact (IEEE division + libdevice exp) cdf on n
  * random finite (endpoint, mu, sigma) triples, far tails included.  example_host: 5 doubles or NULL. */
 int         bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_host, double *example_host);
+/* worst |screening cdf - exact cdf| over n random arguments, in units of 2^-51 (the screening window is 64 units) */
+int         bsw_selftest_cdf_apx(int64_t n, uint64_t seed, double *worst_units_host);
 
 /* ------------------------------------------------------------------------------------------------
  * Stream sets: B device-resident ANS states.

@@ -374,3 +374,13 @@ def test_two_phase_abi_extreme_tables_vs_fused_and_oracle(S, q, full):
         st, s_ = a.decode(O.CState.from_list(states[b]))
         assert np.array_equal(res["2p"][1][b], s_) and res["2p"][0][b] == st.to_list()
         assert res["2p"][2][b] == a.encode(st, sym[b].astype(np.int64)).to_list()
+
+
+def test_screening_cdf_error_is_far_inside_the_window():
+    """k_rows trusts bsw_cdf_apx only when the scaled pmf is >= 64 units (2^-51 each) away from a truncation boundary;
+    the pmf error is at most twice the cdf error, so the cdf error must stay below 32 units.  Measured worst case over
+    2^27 arguments (bulk, steep part, far tails, sigma down to the x-level minimum) has to be below 8."""
+    worst = ctypes.c_double(0)
+    check(lib().bsw_selftest_cdf_apx(1 << 27, 777, ctypes.byref(worst)))
+    print("worst |apx - exact| =", worst.value, "units of 2^-51")
+    assert worst.value < 8.0
