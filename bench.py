@@ -403,8 +403,10 @@ def main():
                 "share_of_step": kernels[dom]["share"]}
     if "fp64" in kernels[dom]:
         roofline["fp64"] = kernels[dom]["fp64"]
-        roofline["note"] = ("the coder's row-table kernel is FP64-pipe bound by construction ((S-1) float64 sigmoids per symbol-op, "
-                            "SURVEY.md 8d/H2): the hbm fraction is the contract's figure, the fp64 fraction is the meaningful one")
+        roofline["note"] = ("the coder's row-table kernel is bound by float64 arithmetic, not HBM ((S-1) float64 sigmoids per symbol-op, "
+                            "SURVEY.md 8d/H2): the hbm fraction is the contract's figure; the fp64 fraction counts 16 FP64 instructions per "
+                            "sigmoid against the measured DFMA peak -- a warp-wide FP64 instruction takes two issue slots, so ~0.5 means half of "
+                            "all issue slots are FP64 and the rest is the kernel's integer work (DESIGN.md 5.1)")
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -124,7 +124,8 @@ __device__ __forceinline__ bool mbar_try_wait_r(uint64_t *bar, uint32_t parity) 
 
 // exact integer pmf (before the +1) of bin j of this lane's block: the rare path of the screened kernel
 template <int NB, int STRIDE>
-__device__ __noinline__ uint32_t rows_exact_pm(const double *tile, int lane, int j, double m, double s, double rs, double mult) {
+__device__ __noinline__ uint32_t rows_exact_pm(const double *tile, int lane, int j0, int t, double m, double s, double rs, double mult) {
+    const int j = j0 + t;                                 // (added here so that the hot loop does not carry j0+1..j0+3)
     const double c = bsw_cdf_fast(tile[lane * STRIDE + j], m, s, rs);
     double p = 0.0;                                       // lower edge of bin 0 is cdf = 0 (cifar_compress.py:184)
     if (j > 0) p = bsw_cdf_fast(tile[lane * STRIDE + j - 1], m, s, rs);
@@ -137,11 +138,11 @@ __device__ __noinline__ uint32_t rows_exact_pm(const double *tile, int lane, int
 // BSW_APX_WINDOW of an integer boundary (about 1.2e-4 of them) is recomputed with the exact bsw_cdf_fast.  The integers
 // this kernel emits are therefore those of the exact function, which is what k_pop_coarse re-evaluates and what the
 // fused kernels produce.  APX = false (BSW_ROWS_EXACT=1) evaluates the exact function for every bin.
-template <int NB, bool POP, bool USE_TMA, bool APX>
+template <int NB, bool POP, bool USE_TMA, bool APX, bool FULLT>
 __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint4 *__restrict__ pairs, uint32_t *__restrict__ coarse,
-        uint2 *__restrict__ fix, uint32_t *__restrict__ pfull) {
+        uint2 *__restrict__ fix, uint32_t *__restrict__ pfull, const BswApxRegs KA) {
     constexpr int S = 32 * NB;
     using RT = RowTile<NB, USE_TMA>;
     __shared__ __align__(16) double tile[RT::DOUBLES];
@@ -183,8 +184,7 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     const int owner = sy / NB, js = sy - owner * NB;     // push: lane and in-lane position of the coded symbol
 
     BswExpRegs K;
-    BswApxRegs KA;
-    if (APX) KA.load(); else K.load();
+    if (!APX) K.load();
     const double *my = tile + lane * RT::STRIDE;
     const uint32_t tl = smem_u32r(t32) + 8u * lane;
     // The screening cdf needs |t| <= 690 (its exponent arithmetic has no range checks).  Rows are sorted, so if both ends
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     // pop, small batches: also keep every integer pmf of the row (before the remnant) so that the serial phase needs no
     // float64 work at all (k_pop_full); written as one 16-byte store per 4 bins
     constexpr int G = NB >= 4 ? 4 : NB;                  // bins per group
-    uint32_t *prow = (POP && pfull) ? pfull + ((int64_t)si * L + row) * S + lane * NB : nullptr;
+    uint32_t *prow = (POP && FULLT) ? pfull + ((int64_t)si * L + row) * S + lane * NB : nullptr;
     // running state of my block: sum, the group holding the (first) maximum, and for push the integer cdf below the symbol
     uint32_t lsum = 0, lbest = 0, pre = 0, pv = 0;
     uint32_t bestv[G];
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
             const bool all = !(all_hi & 0x80000000u);
 #pragma unroll
             for (int t = 0; t < G; ++t)
-                if (doubt[t] || all) vv[t] = rows_exact_pm<NB, RT::STRIDE>(tile, lane, j0 + t, m, s, rs, mult) + 1u;
+                if (doubt[t] || all) vv[t] = rows_exact_pm<NB, RT::STRIDE>(tile, lane, j0, t, m, s, rs, mult) + 1u;
         }
         uint32_t gsum = 0, gmax = 0;
 #pragma unroll
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
                 }
             }
         }
-        if (POP && prow) {
+        if (POP && FULLT) {
             if (G == 4) *reinterpret_cast<uint4 *>(prow + j0) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
             else for (int t = 0; t < G; ++t) prow[j0 + t] = vv[t];
         }
@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
         if (lane >= o) incl += t;
     }
     const uint32_t total = __shfl_sync(FULL, incl, 31);
-    int bi = lane * NB + lbi;
-    warp_argmax(lbest, bi);                               // :35 first maximum of the row
+    // :35 first maximum of the row: lanes own ascending blocks, so it is the lowest lane that holds the row maximum
+    const uint32_t rowmax = __reduce_max_sync(FULL, lbest);
+    const int wl = __ffs(__ballot_sync(FULL, lbest == rowmax)) - 1;
+    const int bi = __shfl_sync(FULL, lane * NB + lbi, wl);
     const uint32_t rem = (1u << bits) - total;
     const int64_t out = (int64_t)si * L + row;
     if (POP) {
@@ -501,19 +503,25 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
     // completing on an mbarrier (BSW_ROWS_TMA=1).  Measured on B200, C8, 1024 streams: 4.53 ms vs 5.40 ms per z level --
     // 256-byte bulk copies are too small to beat two in-flight loads per thread, so TMA staging is the documented option,
     // not the default.
+    const BswApxRegs kp = bsw_apx_params();
     static const bool tma = getenv("BSW_ROWS_TMA") && getenv("BSW_ROWS_TMA")[0] == '1';
     // BSW_ROWS_EXACT=1: evaluate the exact cdf for every bin instead of screening with bsw_cdf_apx (A/B switch; same output)
     static const bool exact = tma || bits > 31 || (getenv("BSW_ROWS_EXACT") && getenv("BSW_ROWS_EXACT")[0] == '1');
     if (phase == 0) {
+#define BSW_ROWS_LAUNCH(POP_, TMA_, APX_, FULL_)                                                                              \
+    k_rows<NB, POP_, TMA_, APX_, FULL_><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, POP_ ? nullptr : sym, bits, q, \
+                                                                  POP_ ? nullptr : pairs, POP_ ? coarse : nullptr,            \
+                                                                  POP_ ? fix : nullptr, POP_ ? pfull : nullptr, kp)
         if (pop) {
-            if (tma) k_rows<NB, true, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
-            else if (exact) k_rows<NB, true, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
-            else k_rows<NB, true, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, pfull);
+            if (tma) { if (full) BSW_ROWS_LAUNCH(true, true, false, true); else BSW_ROWS_LAUNCH(true, true, false, false); }
+            else if (exact) { if (full) BSW_ROWS_LAUNCH(true, false, false, true); else BSW_ROWS_LAUNCH(true, false, false, false); }
+            else { if (full) BSW_ROWS_LAUNCH(true, false, true, true); else BSW_ROWS_LAUNCH(true, false, true, false); }
         } else {
-            if (tma) k_rows<NB, false, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
-            else if (exact) k_rows<NB, false, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
-            else k_rows<NB, false, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, nullptr);
+            if (tma) BSW_ROWS_LAUNCH(false, true, false, false);
+            else if (exact) BSW_ROWS_LAUNCH(false, false, false, false);
+            else BSW_ROWS_LAUNCH(false, false, true, false);
         }
+#undef BSW_ROWS_LAUNCH
     } else {
         if (pop && full) k_pop_full<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, 0);
         else if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
@@ -649,7 +657,7 @@ __global__ void k_cdf_selftest(int64_t n, uint64_t seed, unsigned long long *bad
     }
 }
 // ---- self-test of the screening function: worst |bsw_cdf_apx - bsw_cdf_fast| in units of 2^-51 (what the window is in) ----
-__global__ void k_cdf_apx_selftest(int64_t n, uint64_t seed, unsigned long long *worst_bits) {
+__global__ void k_cdf_apx_selftest(int64_t n, uint64_t seed, unsigned long long *worst_bits, const BswApxRegs kp) {
     __shared__ double t32[BSW_APX_TABLE_DOUBLES];
     bsw_apx_table_fill(t32, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -665,8 +673,7 @@ __global__ void k_cdf_apx_selftest(int64_t n, uint64_t seed, unsigned long long 
     if (mode == 3) e = muf + (nxt() - 0.5) * 8.0 * scf;                  // the steep part of the curve
     if (mode == 7) e = (double)(float)e;
     double sc = (double)scf, mu = (double)muf, rs = __ddiv_rn(1.0, sc);
-    BswApxRegs KA;
-    KA.load();
+    const BswApxRegs KA = kp;
     double a = bsw_cdf_apx<true>(e, mu, rs, smem_u32r(t32) + 8u * (threadIdx.x & 31), KA), b = bsw_cdf_fast(e, mu, sc, rs);
     double err = fabs(a - b) * 2251799813685248.0;                        // 2^51
     if (!(err == err)) err = 1e300;
@@ -677,7 +684,7 @@ extern "C" int bsw_selftest_cdf_apx(int64_t n, uint64_t seed, double *worst_unit
     unsigned long long *w = nullptr;
     BSW_CUDA(cudaMalloc(&w, 8));
     BSW_CUDA(cudaMemset(w, 0, 8));
-    k_cdf_apx_selftest<<<(unsigned)((n + 255) / 256), 256>>>(n, seed, w);
+    k_cdf_apx_selftest<<<(unsigned)((n + 255) / 256), 256>>>(n, seed, w, bsw_apx_params());
     BSW_LAUNCH_CHECK();
     unsigned long long h = 0;
     BSW_CUDA(cudaMemcpy(&h, w, 8, cudaMemcpyDeviceToHost));
