@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--cpu-baseline-images", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="sub-batches coded concurrently on separate CUDA streams (1 = off)")
+    ap.add_argument("--dual-stream", type=int, default=0, help="0 off; 2 = serial coder kernels on a high-priority stream (experiment)")
     ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
     args = ap.parse_args()
 
@@ -242,6 +243,8 @@ def main():
         codec = BitSwapCodec(cfg, model, bins, B)
     two_phase = not args.fused_coder
     codec.set_two_phase(two_phase)
+    if args.dual_stream:
+        codec.set_dual_stream(args.dual_stream)
     ss = StreamSet(B, 4096 + 2048)
     w, head = synthetic.initial_words(4096, seed=100)
     ss.fill(w, head)

@@ -486,6 +486,131 @@ __global__ void __launch_bounds__(BW * 32) k_pop_full(bsw_streams sv, int first,
     ws.close(sv, b, lane);
 }
 
+// ---- phase B: pop with the full table, rows staged through shared memory by bulk copies -------------------------------
+// k_pop_full's critical path per symbol is ballot -> DEPENDENT global load of the 32-bin chunk (300-800 cycles) -> scan ->
+// decode.  Which chunk is needed depends on the head, but which ROW does not: here lane 0 of each warp keeps PD whole rows
+// (S x 4 B each, one cp.async.bulk per row completing on an mbarrier) in flight ahead of the coder, so the chunk read is
+// a shared-memory load.  Price: the serial phase now reads the whole table (S x 4 B per row instead of 128 B).
+constexpr int PD = 4;                                     // rows in flight per warp
+int g_pop_staged = -1;                                    // -1: BSW_POP_STAGED decides (default off), 0/1: bsw_set_pop_staged
+template <int NB>
+__global__ void __launch_bounds__(BW * 32) k_pop_staged(bsw_streams sv, int first, int count, const uint32_t *__restrict__ pfull,
+        const uint32_t *__restrict__ coarse, const uint2 *__restrict__ fix, int16_t *__restrict__ sym, int64_t L, int bits,
+        int shared_tables) {
+    constexpr int S = 32 * NB;
+    extern __shared__ __align__(128) uint8_t stage_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *rows = reinterpret_cast<uint32_t *>(stage_raw) + (size_t)warp * PD * S;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_raw + (size_t)BW * PD * S * 4) + warp * PD;
+    const int si = blockIdx.x * BW + warp;
+    if (si >= count) return;
+    const int b = first + si;
+    WarpStream2 ws;
+    ws.open(sv, b);
+    if (ws.err) return;
+    const int64_t ts = shared_tables ? 0 : si;
+    const uint32_t *cb = coarse + ts * L * NB;
+    const uint32_t *pb = pfull + ts * L * S;
+    const uint2 *fb = fix + ts * L;
+    int16_t *sy = sym + (int64_t)si * L;
+    const uint32_t mask = (uint32_t)(((uint64_t)1 << bits) - 1);
+    if (lane == 0) {
+        for (int d = 0; d < PD; ++d) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32r(&bars[d])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // rows are consumed in the order L-1, L-2, ...; sequence number q <-> row L-1-q, slot q % PD, parity (q / PD) & 1
+    int64_t issued = 0, consumed = 0;
+    auto issue = [&]() {
+        if (lane == 0) {
+            const int slot = (int)(issued % PD);
+            const uint32_t bar = smem_u32r(&bars[slot]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(S * 4)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32r(rows + slot * S)), "l"(pb + (L - 1 - issued) * S), "r"((uint32_t)(S * 4)), "r"(bar) : "memory");
+        }
+        ++issued;
+    };
+    auto wait_row = [&]() {
+        uint64_t *bar = &bars[consumed % PD];
+        const uint32_t parity = (uint32_t)((consumed / PD) & 1);
+        uint32_t spins = 0;
+        while (!mbar_try_wait_r(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
+    };
+    while (issued < PD && issued < L) issue();
+    uint2 fx_w = make_uint2(0, 0), fx_nx;
+    int my_sym = 0;
+    {
+        int64_t r = ((L - 1) & ~(int64_t)31) + lane;
+        fx_nx = r < L ? __ldg(fb + r) : make_uint2(0, 0);
+    }
+    uint32_t base_n1 = (lane < NB) ? __ldg(cb + (L - 1) * NB + lane) : 0xffffffffu;
+    uint32_t base_n2 = (lane < NB && L > 1) ? __ldg(cb + (L - 2) * NB + lane) : 0xffffffffu;
+    for (int64_t i = L - 1; i >= 0; --i) {
+        const int j32 = (int)(i & 31);
+        const bool new_block = (j32 == 31 || i == L - 1);
+        if (new_block) fx_w = fx_nx;
+        const int bi = (int)__shfl_sync(FULL, fx_w.x, j32);
+        const uint32_t rem = __shfl_sync(FULL, fx_w.y, j32);
+        if (new_block) {
+            int64_t r = (i & ~(int64_t)31) - 32 + lane;
+            fx_nx = r >= 0 ? __ldg(fb + r) : make_uint2(0, 0);
+        }
+        const uint32_t base = base_n1;
+        base_n1 = base_n2;
+        if (i > 1) base_n2 = (lane < NB) ? __ldg(cb + (i - 2) * NB + lane) : 0xffffffffu;
+        const uint32_t mm = (uint32_t)ws.x & mask;                                       // cifar_compress.py:60
+        const int chunk = 31 - __clz(__ballot_sync(FULL, base <= mm));
+        const int k = chunk * 32 + lane;
+        wait_row();
+        uint32_t v = rows[(consumed % PD) * S + k] + (k == bi ? rem : 0u);
+        __syncwarp();                                     // every lane has read the slot: lane 0 may refill it
+        if (issued < L) issue();
+        ++consumed;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t cex = __shfl_sync(FULL, base, chunk) + incl - v;
+        const int js = 31 - __clz(__ballot_sync(FULL, cex <= mm));                       // :61
+        const uint32_t ps = __shfl_sync(FULL, v, js), cs = __shfl_sync(FULL, cex, js);
+        if (lane == j32) my_sym = chunk * 32 + js;                                       // :62
+        ws.decode(ps, cs, mm, bits, lane);                                               // :63-65
+        if (j32 == 0 || ws.err) {
+            int64_t r = (i & ~(int64_t)31) + lane;
+            if (r < L && r >= i) sy[r] = (int16_t)my_sym;
+            if (ws.err) break;
+        }
+    }
+    while (consumed < issued) { wait_row(); ++consumed; }     // (error exit: let the copies in flight land before the warp leaves)
+    ws.close(sv, b, lane);
+}
+template <int NB>
+int launch_pop_full(bsw_streams *s, int first, int count, const uint32_t *pfull, const uint32_t *coarse, const uint2 *fix,
+                    int16_t *sym, int64_t L, int bits, int shared_tables, cudaStream_t st) {
+    // Measured on B200 (C8): at 1024 streams the staged kernel takes 1.41 ms per level against 1.66 ms (k_pop_full) and
+    // 2.55 ms (k_pop_coarse), but it reads the whole 8.6 GB table from HBM; with 4 lanes in flight that traffic (and its
+    // power) costs more than the shorter serial phase returns: 311 ms per step against 299 ms.  Off by default;
+    // BSW_POP_STAGED=1 or bsw_set_pop_staged(1) selects it.
+    static const bool env_staged = getenv("BSW_POP_STAGED") && getenv("BSW_POP_STAGED")[0] == '1';
+    const bool staged = g_pop_staged >= 0 ? g_pop_staged != 0 : env_staged;
+    const dim3 grid((count + BW - 1) / BW);
+    if (staged) {
+        constexpr int SMEM = BW * PD * 32 * NB * 4 + BW * PD * 8;
+        static bool attr_done = false;
+        if (!attr_done) {
+            BSW_CUDA(cudaFuncSetAttribute(k_pop_staged<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+            attr_done = true;
+        }
+        k_pop_staged<NB><<<grid, BW * 32, SMEM, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, shared_tables);
+    } else {
+        k_pop_full<NB><<<grid, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, shared_tables);
+    }
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+
 template <int NB>
 int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
                 int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int bits, int q, void *scratch,
@@ -523,7 +648,7 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
         }
 #undef BSW_ROWS_LAUNCH
     } else {
-        if (pop && full) k_pop_full<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, 0);
+        if (pop && full) return launch_pop_full<NB>(s, first, count, pfull, coarse, fix, sym, L, bits, 0, st);
         else if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
         else k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pairs, L, bits);
     }
@@ -553,16 +678,13 @@ int bsw_prior_coarse(const uint32_t *C, int64_t L, int S, uint32_t *coarse, uint
 int bsw_pop_shared_table(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *coarse, const uint2 *fix,
                          int16_t *sym, int64_t L, int S, int bits, cudaStream_t st) {
     BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B, "stream range out of bounds");
-    dim3 grid((count + BW - 1) / BW);
     switch (S) {
-        case 128:  k_pop_full<4><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
-        case 256:  k_pop_full<8><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
-        case 512:  k_pop_full<16><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
-        case 1024: k_pop_full<32><<<grid, BW * 32, 0, st>>>(*s, first, count, P, coarse, fix, sym, L, bits, 1); break;
-        default: return BSW_E_INVALID;
+        case 128:  return launch_pop_full<4>(s, first, count, P, coarse, fix, sym, L, bits, 1, st);
+        case 256:  return launch_pop_full<8>(s, first, count, P, coarse, fix, sym, L, bits, 1, st);
+        case 512:  return launch_pop_full<16>(s, first, count, P, coarse, fix, sym, L, bits, 1, st);
+        case 1024: return launch_pop_full<32>(s, first, count, P, coarse, fix, sym, L, bits, 1, st);
     }
-    BSW_LAUNCH_CHECK();
-    return BSW_OK;
+    return BSW_E_INVALID;
 }
 
 // Scratch bytes for the two-phase coder for `count` streams of L rows with support S: `full` adds room for the whole
@@ -709,6 +831,8 @@ extern "C" int bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_ho
     *mismatches_host = (int64_t)h;
     return BSW_OK;
 }
+
+extern "C" int bsw_set_pop_staged(int on) { g_pop_staged = on < 0 ? -1 : (on ? 1 : 0); return BSW_OK; }
 
 // ---- C ABI of the two-phase coder (same contract as bsw_logistic_push/pop + caller-provided scratch) -----------------
 extern "C" int64_t bsw_logistic_scratch_bytes(int count, int64_t L, int S, int full_tables) {

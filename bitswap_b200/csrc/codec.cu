@@ -131,7 +131,7 @@ extern "C" int64_t bsw_codec_last_launches(const bsw_codec *c) { return c ? c->l
  * 0 (default): everything on the caller's stream. */
 extern "C" int bsw_codec_set_dual_stream(bsw_codec *c, int on) {
     BSW_REQUIRE(c, "null codec");
-    c->dual_stream = on ? 1 : 0;
+    c->dual_stream = on < 0 ? 0 : (on > 2 ? 2 : on);
     return BSW_OK;
 }
 
@@ -166,10 +166,15 @@ struct Ctx {
         cudaStreamWaitEvent(target, e, 0);
         st = target;
     }
-    void begin(cudaStream_t user) { caller = user; st = user; if (c->dual_stream) use(c->st_lo); }
+    // dual_stream 1: convs on the high-priority internal stream, coder kernels on the low-priority one (measured: slower).
+    // dual_stream 2: only the serial phase-B coder kernels (one warp per stream, latency-bound, a few hundred small CTAs) move
+    //   to the high-priority stream, so that in a multi-lane run their CTAs are dispatched ahead of the queued throughput
+    //   CTAs of the other lanes instead of waiting behind a k_rows grid that owns every register of every SM.
+    void begin(cudaStream_t user) { caller = user; st = user; if (c->dual_stream == 1) use(c->st_lo); }
     void end() { use(caller); }
-    void conv_stream() { if (c->dual_stream) use(c->st_hi); }
-    void coder_stream() { if (c->dual_stream) use(c->st_lo); }
+    void conv_stream() { if (c->dual_stream == 1) use(c->st_hi); else if (c->dual_stream == 2) use(caller); }
+    void coder_stream() { if (c->dual_stream == 1) use(c->st_lo); else if (c->dual_stream == 2) use(caller); }
+    void serial_stream() { if (c->dual_stream == 2) use(c->st_hi); }
     const double *zend(int lvl) const { return c->b->zend + (size_t)lvl * c->zdim * c->S; }
     int infer(int zi) { conv_stream(); return bsw_model_run(c->m, true, zi, c->given, count, c->mu, c->scale, 1, st, &nl, &c->prof); }
     int generate(int zi) { conv_stream(); return bsw_model_run(c->m, false, zi, c->given, count, c->mu, c->scale, 0, st, &nl, &c->prof); }
@@ -205,6 +210,7 @@ struct Ctx {
         int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
+        serial_stream();
         c->prof.begin(CAT_POP_Z, st);
         rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
@@ -224,6 +230,7 @@ struct Ctx {
         int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
+        serial_stream();
         c->prof.begin(CAT_PUSH_Z, st);
         rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
@@ -245,6 +252,7 @@ struct Ctx {
         int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
+        serial_stream();
         c->prof.begin(CAT_POP_X, st);
         rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
@@ -264,6 +272,7 @@ struct Ctx {
         int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
+        serial_stream();
         c->prof.begin(CAT_PUSH_X, st);
         rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
@@ -271,6 +280,7 @@ struct Ctx {
     }
     int push_prior(const int16_t *sym) {
         coder_stream();
+        serial_stream();
         ++nl;
         c->prof.begin(CAT_PRIOR, st);
         int rc = bsw_ans_push_i16(s, first, count, c->priorP, c->priorC, 0, 0, sym, c->zdim, c->S, 31, st);
@@ -279,6 +289,7 @@ struct Ctx {
     }
     int pop_prior(int16_t *sym) {
         coder_stream();
+        serial_stream();
         ++nl;
         c->prof.begin(CAT_PRIOR, st);
         int rc = c->priorCoarse

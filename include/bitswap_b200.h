@@ -153,6 +153,9 @@ int bsw_logistic_pop(bsw_streams *s, int first, int count, const float *mu_dev, 
  * bsw_logistic_scratch_bytes(count, L, S, 0) bytes.  With bsw_logistic_scratch_bytes(count, L, S, 1) bytes the pop
  * keeps the whole integer table of the level and its serial phase needs no float64 work (small batches). */
 int64_t bsw_logistic_scratch_bytes(int count, int64_t L, int S, int full_tables);
+/* Full-table pops: 1 = serial phase with rows staged through shared memory by bulk copies (shorter critical path, reads the
+ * whole table), 0 = dependent 128-byte loads (default), -1 = let the BSW_POP_STAGED environment variable decide. */
+int bsw_set_pop_staged(int on);
 int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
                          const float *scale_dev, int64_t scale_stream_stride, const double *endpoints_dev,
                          int64_t endp_row_stride, const int16_t *sym_dev, int64_t L, int S, int bits, int quantbits,

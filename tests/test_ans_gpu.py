@@ -315,11 +315,14 @@ def _pad_big(ends):
     return out
 
 
-@pytest.mark.parametrize("S,q,full", [(1024, 10, 0), (1024, 10, 1), (256, 8, 1), (128, 7, 0), (64, 6, 0), (32, 5, 0)])
+@pytest.mark.parametrize("S,q,full", [(1024, 10, 0), (1024, 10, 1), (1024, 10, 2), (256, 8, 1), (256, 8, 2), (128, 7, 0), (128, 7, 2),
+                                      (64, 6, 0), (32, 5, 0)])
 def test_two_phase_abi_extreme_tables_vs_fused_and_oracle(S, q, full):
     """Two-phase coder through the C ABI against the fused kernels and the oracle (fed our exact pmfs), on hostile rows:
     sigma at the x-level minimum (2/255/8) so that almost every bin is a saturated tail (P = 1, huge remnant), means far
     outside the bin range, symbols in the dead tails, plus ordinary rows."""
+    staged, full = int(full == 2), int(full > 0)         # full == 2: full tables + the bulk-copy staged serial phase
+    check(lib().bsw_set_pop_staged(staged))
     rs = np.random.RandomState(S + full)
     B, L = 9, 96
     lo, hi = -6 - rs.uniform(0, 1, L), 6 + rs.uniform(0, 1, L)
@@ -368,6 +371,7 @@ def test_two_phase_abi_extreme_tables_vs_fused_and_oracle(S, q, full):
                                           L, S, 31, q, cuda_stream_ptr()))
         ss.raise_on_error()
         res[name] = (after_pop, popped, ss.export_lists())
+    check(lib().bsw_set_pop_staged(-1))
     assert res["2p"][0] == res["fused"][0] and np.array_equal(res["2p"][1], res["fused"][1]) and res["2p"][2] == res["fused"][2]
     for b in range(B):
         a = O.AnsC(tables=tabs[b])
