@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--cpu-baseline-images", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="sub-batches coded concurrently on separate CUDA streams (1 = off)")
+    ap.add_argument("--lane-size", type=int, default=0, help="streams per lane (0 = batch/lanes); the last lane takes the remainder")
     ap.add_argument("--dual-stream", type=int, default=0, help="0 off; 2 = serial coder kernels on a high-priority stream (experiment)")
     ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
     args = ap.parse_args()
@@ -236,7 +237,7 @@ def main():
     bins = Bins(cfg, zend, zcen)
     if args.lanes > 1:
         from bitswap_b200.codec import PipelinedCodec
-        codec = PipelinedCodec(cfg, sd, bins, B, lanes=args.lanes, use_tensor_cores=bool(use_tc))
+        codec = PipelinedCodec(cfg, sd, bins, B, lanes=args.lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size)
     else:
         model = Model.from_config(cfg, max_batch=B, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
         model.compress()

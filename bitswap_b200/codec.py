@@ -104,10 +104,13 @@ class PipelinedCodec:
     help).  Results are identical to a single BitSwapCodec: every stream is independent and every kernel is
     batch-invariant.  Each lane owns a model replica (activations are per-lane anyway)."""
 
-    def __init__(self, cfg: CodecConfig, state_dict, bins: Bins, max_batch: int, lanes: int = 4, use_tensor_cores=True):
+    def __init__(self, cfg: CodecConfig, state_dict, bins: Bins, max_batch: int, lanes: int = 4, use_tensor_cores=True, lane_size: int = 0):
         self.cfg, self.bins, self.max_batch = cfg, bins, int(max_batch)
         self.lanes = max(1, min(int(lanes), self.max_batch))
         self.per = -(-self.max_batch // self.lanes)
+        if lane_size > 0:             # explicit sub-batch size (the last lane takes the remainder), e.g. a multiple of SMs/2
+            self.per = min(int(lane_size), self.max_batch)
+            self.lanes = -(-self.max_batch // self.per)
         self.models, self.codecs, self.streams = [], [], []
         self.serial = False          # True: run the lanes back to back on the current stream (clean per-kernel timing)
         for _ in range(self.lanes):
