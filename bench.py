@@ -173,7 +173,7 @@ def run_reference_arm(args, cfg, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * (t_enc + t_dec) / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 tables / f32 nets / int64 coder", "data": "synthetic",
-            "config": {"workload": f"{args.config}: CIFAR-shaped 32x32x3 uint8, nz={cfg.nz}, W={cfg.reswidth}; {sample}",
+            "config": {"workload": f"{args.config}: {cfg.xs[1]}x{cfg.xs[2]}x{cfg.xs[0]} uint8, nz={cfg.nz}, W={cfg.reswidth}; {sample}",
                        "what_runs": "oracle port of the reference path (torch-CPU nets, torch float64 logistic tables, "
                                     "Python-loop ANS with Python ints) -- the reference itself is pure Python and cannot travel"},
             "encode_Mpixel_s": args.steps * nimg * 1024 / t_enc / 1e6, "decode_Mpixel_s": args.steps * nimg * 1024 / t_dec / 1e6,
@@ -418,7 +418,7 @@ def main():
             "coder": "two-phase (parallel f64 row tables + serial integer coder)" if two_phase else "fused one-warp-per-stream",
             "lanes": args.lanes,
             "data": "synthetic",
-            "config": {"workload": f"{args.config}: CIFAR-shaped 32x32x3 uint8, nz={cfg.nz}, W={cfg.reswidth}, q={cfg.quantbits}; "
+            "config": {"workload": f"{args.config}: {cfg.xs[1]}x{cfg.xs[2]}x{cfg.xs[0]} uint8, nz={cfg.nz}, W={cfg.reswidth}, q={cfg.quantbits}; "
                                    f"{B} independent ANS streams per GPU x 1 image per step; step = Bit-Swap encode + decode",
                        "streams_per_gpu": B, "global_batch": B * world, "weights": "seeded random init (reference default-init distribution)",
                        "bins": "synthetic uniform grids + float32 equal-mass top level", "images": "iid uniform uint8",
