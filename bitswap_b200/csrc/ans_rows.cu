@@ -85,14 +85,6 @@ struct WarpStream2 {          // same state handling as ans_kernels.cu's WarpStr
     }
 };
 
-__device__ __forceinline__ void warp_argmax(uint32_t &val, int &idx) {       // first index wins ties (cifar_compress.py:35)
-    for (int o = 16; o; o >>= 1) {
-        uint32_t ov = __shfl_xor_sync(FULL, val, o);
-        int oi = __shfl_xor_sync(FULL, idx, o);
-        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-    }
-}
-
 constexpr int RW = 16;       // warps per CTA in phase A: 512 threads x <=64 registers = half an SM's register file, so two
                              // of these CTAs fill an SM, or one of them sits beside one k_conv_tc CTA (codec.cu overlap)
 
