@@ -332,6 +332,7 @@ k_conv_tc_c2(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant_
 // resident per SM and one's epilogue runs under the other's MMAs.  Price: the weight tile is fetched per half image
 // (L2->SM bytes per k-block and MMA row 48 KB/256 rows -> 32 KB/128 rows); the order of the k-blocks and of the MMAs
 // into each accumulator is unchanged, so results are bit-identical to the full-tile kernel.
+template <bool COAL>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_conv_tc_h(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
             const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
@@ -413,6 +414,61 @@ k_conv_tc_h(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__
         mbar_wait(acc_bar, 0);
         tc_fence_after();
         const int64_t row = ((int64_t)img * 256 + p) * 256;
+        if (COAL) {
+            // Coalesced epilogue.  tcgen05.ld hands every lane one pixel's 32 consecutive channels; written straight to
+            // HBM that is 32 scattered 16-byte pieces per store instruction (the LSU, not HBM, bounds the direct epilogue:
+            // ncu shows lg_throttle on every STG).  Instead the warp transposes each 32 px x 32 ch chunk through a private
+            // padded tile in the (now idle) pipeline stages, so that 8 consecutive lanes hold 128 contiguous bytes of one
+            // pixel row: residual loads, trunk stores and plane stores become 4 full lines per instruction.
+            float *tile = reinterpret_cast<float *>(smem) + ew * (32 * 36);          // 32 rows x 36 floats (144 B stride)
+            const int rsub = lane >> 3, col4 = (lane & 7) * 4;
+#pragma unroll 1
+            for (int cc = chalf * 64; cc < chalf * 64 + 64; cc += 32) {
+                const int c0 = co0 + cc;
+                {
+                    uint32_t rr[32], rc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc, rr);
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + BN + cc, rc);
+                    float4 *trow = reinterpret_cast<float4 *>(tile + lane * 36);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        trow[i] = make_float4(__uint_as_float(rr[4 * i]) + __uint_as_float(rc[4 * i]),
+                                              __uint_as_float(rr[4 * i + 1]) + __uint_as_float(rc[4 * i + 1]),
+                                              __uint_as_float(rr[4 * i + 2]) + __uint_as_float(rc[4 * i + 2]),
+                                              __uint_as_float(rr[4 * i + 3]) + __uint_as_float(rc[4 * i + 3]));
+                }
+                __syncwarp();
+                const float4 bq = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + col4));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 4 * k + rsub;
+                    const int64_t prow = ((int64_t)img * 256 + mh * 128 + quad * 32 + r) * 256 + c0 + col4;
+                    float4 x = *reinterpret_cast<const float4 *>(tile + r * 36 + col4);
+                    x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;      // same order as the direct path: (main+cross)+bias
+                    if (a.resid) {
+                        const float4 q = *reinterpret_cast<const float4 *>(a.resid + prow);
+                        x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+                    }
+                    if (a.T_elu) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+                    if (a.T) *reinterpret_cast<float4 *>(a.T + prow) = x;
+                    if (a.A_hi) {
+                        float y[4] = {x.x, x.y, x.z, x.w};
+                        uint32_t hi[2], lo[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float x0 = a.A_elu ? elu1(y[2 * i]) : y[2 * i], x1 = a.A_elu ? elu1(y[2 * i + 1]) : y[2 * i + 1];
+                            __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                            __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        *reinterpret_cast<uint2 *>(a.A_hi + prow) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2 *>(a.A_lo + prow) = make_uint2(lo[0], lo[1]);
+                    }
+                }
+                __syncwarp();                             // the tile is rewritten by the next chunk
+            }
+        } else
 #pragma unroll 1
         for (int cc = chalf * 64; cc < chalf * 64 + 64; cc += 32) {
             const int c0 = co0 + cc;
@@ -599,7 +655,8 @@ int bsw_model_tc_prepare(bsw_model *m) {
     m->tc_slots = slots;
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     m->tc_ready = true;
     return BSW_OK;
 }
@@ -653,7 +710,7 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     // weight tiles cost the 5x5.  Full tile stays the default here; BSW_TC_HALFTILE=1 selects the other one.
     static const bool half_tile = getenv("BSW_TC_HALFTILE") && getenv("BSW_TC_HALFTILE")[0] == '1';
     if (!use_cluster && half_tile)
-        k_conv_tc_h<<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
+        k_conv_tc_h<true><<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
                                                                                    s.map_hi, s.map_lo, t);
     else if (use_cluster)
         k_conv_tc_c2<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
@@ -683,7 +740,12 @@ int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n
     t.A_elu = a.A_elu;
     static const bool full_tile = getenv("BSW_TC_FULLTILE") && getenv("BSW_TC_FULLTILE")[0] == '1';
     if (full_tile) k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
-    else k_conv_tc_h<<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t);
+    else {
+        // BSW_TC_EPI_DIRECT=1: the per-lane (uncoalesced) epilogue, for A/B runs; results are identical
+        static const bool direct = getenv("BSW_TC_EPI_DIRECT") && getenv("BSW_TC_EPI_DIRECT")[0] == '1';
+        if (direct) k_conv_tc_h<false><<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t);
+        else k_conv_tc_h<true><<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t);
+    }
     BSW_LAUNCH_CHECK();
     *launches += 2;
     return BSW_OK;
