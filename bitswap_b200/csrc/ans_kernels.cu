@@ -802,6 +802,7 @@ extern "C" int bsw_logistic_pop(bsw_streams *s, int first, int count, const floa
 // ================================================================================================
 // Bin tables + centre gathers (a5, a6, a7 data)
 // ================================================================================================
+int bsw_rows6_build_meta(const double *endp, int64_t ers, int64_t L, int S, void *meta_dev, int *n_affine_host, cudaStream_t st);   // ans_rows6.cu
 extern "C" int bsw_bins_create(bsw_bins **out, int nz, int zdim, int q, int xdim, const double *zend_host,
                                const double *zcen_host) {
     BSW_REQUIRE(out && nz > 0 && zdim > 0 && q > 0 && q <= 10 && zend_host && zcen_host, "bsw_bins_create: bad arguments");
@@ -826,12 +827,35 @@ extern "C" int bsw_bins_create(bsw_bins **out, int nz, int zdim, int q, int xdim
     for (int k = 1; k <= 255; ++k) xe[k - 1] = (((double)k - 127.5) / 127.5) - 1. / 255.;   // rand.py:146-147
     xe[255] = inf;
     BSW_CUDA(cudaMemcpy(b->xend, xe, sizeof(xe), cudaMemcpyHostToDevice));
+    // classify the rows once: levels whose rows are all uniform grids (every level discretize_kbins() builds,
+    // discretization.py:105-118, and the pixel row) are coded by the affine-row kernels
+    BSW_REQUIRE(nz <= 64, "bsw_bins_create: at most 64 levels");
+    BSW_CUDA(cudaMalloc(&b->zmeta, (size_t)32 * rows));
+    BSW_CUDA(cudaMalloc(&b->xmeta, 32));
+    for (int l = 0; l < nz; ++l) {
+        int n_aff = 0;
+        b->zaffine[l] = 0;
+        if (S >= 8) {
+            if (int rc = bsw_rows6_build_meta(b->zend + (size_t)l * zdim * S, S, zdim, S, (uint8_t *)b->zmeta + (size_t)32 * l * zdim, &n_aff, nullptr)) return rc;
+            b->zaffine[l] = n_aff == zdim;
+        }
+    }
+    {
+        int n_aff = 0;
+        if (int rc = bsw_rows6_build_meta(b->xend, 0, 1, 256, b->xmeta, &n_aff, nullptr)) return rc;
+        b->xaffine = n_aff == 1;
+    }
     *out = b;
     return BSW_OK;
 }
+extern "C" int bsw_bins_level_is_uniform(const bsw_bins *b, int level) {
+    if (!b) return 0;
+    if (level < 0) return b->xaffine;
+    return level < b->nz ? b->zaffine[level] : 0;
+}
 extern "C" int bsw_bins_destroy(bsw_bins *b) {
     if (!b) return BSW_OK;
-    cudaFree(b->zend); cudaFree(b->zcen); cudaFree(b->xend);
+    cudaFree(b->zend); cudaFree(b->zcen); cudaFree(b->xend); cudaFree(b->zmeta); cudaFree(b->xmeta);
     delete b;
     return BSW_OK;
 }

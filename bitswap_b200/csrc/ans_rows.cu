@@ -94,25 +94,15 @@ constexpr int RW = 16;       // warps per CTA in phase A: 512 threads x <=64 reg
 // cdf of the previous bin is already in a register (one shuffle per row instead of two per bin) and the 32-bin chunk
 // totals the pop side needs are lane-local sums (no per-chunk warp reduction).  ~42 issued instructions per cdf value,
 // 27 of them on the FP64 pipe.
-// Tile layout: lane l's NB endpoints are contiguous and start at double index l*(NB+PAD).  PAD = 2 keeps every chunk
-// 16-byte aligned (a TMA bulk-copy requirement) at the price of a 2-way bank conflict on the lane-blocked 8-byte reads
-// (one LDS per cdf value against 27 FP64 instructions: irrelevant).  NB = 1 rows (S = 32) are too small for bulk copies
-// and use plain loads.
-template <int NB, bool USE_TMA>
+// Tile layout: lane l's NB endpoints are contiguous and start at double index l*(NB+1): odd stride, conflict-free for the
+// lane-blocked 8-byte reads.
+template <int NB>
 struct RowTile {
-    static constexpr bool TMA = USE_TMA && NB >= 2;
-    static constexpr int PAD = TMA ? 2 : 1;              // plain staging: odd stride, conflict-free
-    static constexpr int STRIDE = NB + PAD;
+    static constexpr int STRIDE = NB + 1;
     static constexpr int DOUBLES = 32 * STRIDE;
 };
 
 __device__ __forceinline__ uint32_t smem_u32r(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ bool mbar_try_wait_r(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(smem_u32r(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
 
 // exact integer pmf (before the +1) of bin j of this lane's block: the rare path of the screened kernel
 template <int NB, int STRIDE>
@@ -130,41 +120,22 @@ __device__ __noinline__ uint32_t rows_exact_pm(const double *tile, int lane, int
 // BSW_APX_WINDOW of an integer boundary (about 1.2e-4 of them) is recomputed with the exact bsw_cdf_fast.  The integers
 // this kernel emits are therefore those of the exact function, which is what k_pop_coarse re-evaluates and what the
 // fused kernels produce.  APX = false (BSW_ROWS_EXACT=1) evaluates the exact function for every bin.
-template <int NB, bool POP, bool USE_TMA, bool APX, bool FULLT>
+template <int NB, bool POP, bool APX>
 __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const int16_t *__restrict__ sym, int bits, int q, uint4 *__restrict__ pairs, uint32_t *__restrict__ coarse,
-        uint2 *__restrict__ fix, uint32_t *__restrict__ pfull, const BswApxRegs KA) {
+        uint2 *__restrict__ fix, const BswApxRegs KA) {
     constexpr int S = 32 * NB;
-    using RT = RowTile<NB, USE_TMA>;
+    using RT = RowTile<NB>;
     __shared__ __align__(16) double tile[RT::DOUBLES];
     __shared__ __align__(16) double t32[APX ? BSW_APX_TABLE_DOUBLES : 2];
-    __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = blockIdx.x;                      // row index i within the level
     const int si = blockIdx.y * RW + warp;               // stream
     const double *e = endp + row * ers;
     if (APX) bsw_apx_table_fill(t32, threadIdx.x, RW * 32);
-    if (RT::TMA) {
-        // TMA-staged endpoint tile: 32 bulk copies (one per lane-chunk, NB*8 bytes each) complete on one mbarrier
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32r(&bar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (warp == 0) {
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32r(&bar)), "r"((uint32_t)(S * 8)) : "memory");
-            __syncwarp();
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32r(tile + lane * RT::STRIDE)), "l"(e + lane * NB), "r"((uint32_t)(NB * 8)), "r"(smem_u32r(&bar)) : "memory");
-        }
-        uint32_t spins = 0;
-        while (!mbar_try_wait_r(&bar, 0)) { if (++spins > (1u << 22)) __trap(); }
-    } else {
-        for (int k = threadIdx.x; k < S; k += RW * 32) tile[(k / NB) * RT::STRIDE + (k % NB)] = __ldg(e + k);
-        __syncthreads();
-    }
+    for (int k = threadIdx.x; k < S; k += RW * 32) tile[(k / NB) * RT::STRIDE + (k % NB)] = __ldg(e + k);
+    __syncthreads();
     if (si >= count) return;
     const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];
     const double rs = __ddiv_rn(1.0, s);
@@ -198,10 +169,7 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
     const double c_last = cdf_at(NB - 1, std::true_type{});
     const double up = __shfl_up_sync(FULL, c_last, 1);
     double prev = lane == 0 ? 0.0 : up;
-    // pop, small batches: also keep every integer pmf of the row (before the remnant) so that the serial phase needs no
-    // float64 work at all (k_pop_full); written as one 16-byte store per 4 bins
     constexpr int G = NB >= 4 ? 4 : NB;                  // bins per group
-    uint32_t *prow = (POP && FULLT) ? pfull + ((int64_t)si * L + row) * S + lane * NB : nullptr;
     // running state of my block: sum, the group holding the (first) maximum, and for push the integer cdf below the symbol
     uint32_t lsum = 0, lbest = 0, pre = 0, pv = 0;
     uint32_t bestv[G];
@@ -256,10 +224,6 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
                     if (j0 + t == js) pv = vv[t];
                 }
             }
-        }
-        if (POP && FULLT) {
-            if (G == 4) *reinterpret_cast<uint4 *>(prow + j0) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-            else for (int t = 0; t < G; ++t) prow[j0 + t] = vv[t];
         }
     };
     if (wide) {
@@ -478,127 +442,10 @@ __global__ void __launch_bounds__(BW * 32) k_pop_full(bsw_streams sv, int first,
     ws.close(sv, b, lane);
 }
 
-// ---- phase B: pop with the full table, rows staged through shared memory by bulk copies -------------------------------
-// k_pop_full's critical path per symbol is ballot -> DEPENDENT global load of the 32-bin chunk (300-800 cycles) -> scan ->
-// decode.  Which chunk is needed depends on the head, but which ROW does not: here lane 0 of each warp keeps PD whole rows
-// (S x 4 B each, one cp.async.bulk per row completing on an mbarrier) in flight ahead of the coder, so the chunk read is
-// a shared-memory load.  Price: the serial phase now reads the whole table (S x 4 B per row instead of 128 B).
-constexpr int PD = 4;                                     // rows in flight per warp
-int g_pop_staged = -1;                                    // -1: BSW_POP_STAGED decides (default off), 0/1: bsw_set_pop_staged
-template <int NB>
-__global__ void __launch_bounds__(BW * 32) k_pop_staged(bsw_streams sv, int first, int count, const uint32_t *__restrict__ pfull,
-        const uint32_t *__restrict__ coarse, const uint2 *__restrict__ fix, int16_t *__restrict__ sym, int64_t L, int bits,
-        int shared_tables) {
-    constexpr int S = 32 * NB;
-    extern __shared__ __align__(128) uint8_t stage_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *rows = reinterpret_cast<uint32_t *>(stage_raw) + (size_t)warp * PD * S;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_raw + (size_t)BW * PD * S * 4) + warp * PD;
-    const int si = blockIdx.x * BW + warp;
-    if (si >= count) return;
-    const int b = first + si;
-    WarpStream2 ws;
-    ws.open(sv, b);
-    if (ws.err) return;
-    const int64_t ts = shared_tables ? 0 : si;
-    const uint32_t *cb = coarse + ts * L * NB;
-    const uint32_t *pb = pfull + ts * L * S;
-    const uint2 *fb = fix + ts * L;
-    int16_t *sy = sym + (int64_t)si * L;
-    const uint32_t mask = (uint32_t)(((uint64_t)1 << bits) - 1);
-    if (lane == 0) {
-        for (int d = 0; d < PD; ++d) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32r(&bars[d])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    // rows are consumed in the order L-1, L-2, ...; sequence number q <-> row L-1-q, slot q % PD, parity (q / PD) & 1
-    int64_t issued = 0, consumed = 0;
-    auto issue = [&]() {
-        if (lane == 0) {
-            const int slot = (int)(issued % PD);
-            const uint32_t bar = smem_u32r(&bars[slot]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(S * 4)) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32r(rows + slot * S)), "l"(pb + (L - 1 - issued) * S), "r"((uint32_t)(S * 4)), "r"(bar) : "memory");
-        }
-        ++issued;
-    };
-    auto wait_row = [&]() {
-        uint64_t *bar = &bars[consumed % PD];
-        const uint32_t parity = (uint32_t)((consumed / PD) & 1);
-        uint32_t spins = 0;
-        while (!mbar_try_wait_r(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
-    };
-    while (issued < PD && issued < L) issue();
-    uint2 fx_w = make_uint2(0, 0), fx_nx;
-    int my_sym = 0;
-    {
-        int64_t r = ((L - 1) & ~(int64_t)31) + lane;
-        fx_nx = r < L ? __ldg(fb + r) : make_uint2(0, 0);
-    }
-    uint32_t base_n1 = (lane < NB) ? __ldg(cb + (L - 1) * NB + lane) : 0xffffffffu;
-    uint32_t base_n2 = (lane < NB && L > 1) ? __ldg(cb + (L - 2) * NB + lane) : 0xffffffffu;
-    for (int64_t i = L - 1; i >= 0; --i) {
-        const int j32 = (int)(i & 31);
-        const bool new_block = (j32 == 31 || i == L - 1);
-        if (new_block) fx_w = fx_nx;
-        const int bi = (int)__shfl_sync(FULL, fx_w.x, j32);
-        const uint32_t rem = __shfl_sync(FULL, fx_w.y, j32);
-        if (new_block) {
-            int64_t r = (i & ~(int64_t)31) - 32 + lane;
-            fx_nx = r >= 0 ? __ldg(fb + r) : make_uint2(0, 0);
-        }
-        const uint32_t base = base_n1;
-        base_n1 = base_n2;
-        if (i > 1) base_n2 = (lane < NB) ? __ldg(cb + (i - 2) * NB + lane) : 0xffffffffu;
-        const uint32_t mm = (uint32_t)ws.x & mask;                                       // cifar_compress.py:60
-        const int chunk = 31 - __clz(__ballot_sync(FULL, base <= mm));
-        const int k = chunk * 32 + lane;
-        wait_row();
-        uint32_t v = rows[(consumed % PD) * S + k] + (k == bi ? rem : 0u);
-        __syncwarp();                                     // every lane has read the slot: lane 0 may refill it
-        if (issued < L) issue();
-        ++consumed;
-        uint32_t incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const uint32_t cex = __shfl_sync(FULL, base, chunk) + incl - v;
-        const int js = 31 - __clz(__ballot_sync(FULL, cex <= mm));                       // :61
-        const uint32_t ps = __shfl_sync(FULL, v, js), cs = __shfl_sync(FULL, cex, js);
-        if (lane == j32) my_sym = chunk * 32 + js;                                       // :62
-        ws.decode(ps, cs, mm, bits, lane);                                               // :63-65
-        if (j32 == 0 || ws.err) {
-            int64_t r = (i & ~(int64_t)31) + lane;
-            if (r < L && r >= i) sy[r] = (int16_t)my_sym;
-            if (ws.err) break;
-        }
-    }
-    while (consumed < issued) { wait_row(); ++consumed; }     // (error exit: let the copies in flight land before the warp leaves)
-    ws.close(sv, b, lane);
-}
 template <int NB>
 int launch_pop_full(bsw_streams *s, int first, int count, const uint32_t *pfull, const uint32_t *coarse, const uint2 *fix,
                     int16_t *sym, int64_t L, int bits, int shared_tables, cudaStream_t st) {
-    // Measured on B200 (C8): at 1024 streams the staged kernel takes 1.41 ms per level against 1.66 ms (k_pop_full) and
-    // 2.55 ms (k_pop_coarse), but it reads the whole 8.6 GB table from HBM; with 4 lanes in flight that traffic (and its
-    // power) costs more than the shorter serial phase returns: 311 ms per step against 299 ms.  Off by default;
-    // BSW_POP_STAGED=1 or bsw_set_pop_staged(1) selects it.
-    static const bool env_staged = getenv("BSW_POP_STAGED") && getenv("BSW_POP_STAGED")[0] == '1';
-    const bool staged = g_pop_staged >= 0 ? g_pop_staged != 0 : env_staged;
-    const dim3 grid((count + BW - 1) / BW);
-    if (staged) {
-        constexpr int SMEM = BW * PD * 32 * NB * 4 + BW * PD * 8;
-        static bool attr_done = false;
-        if (!attr_done) {
-            BSW_CUDA(cudaFuncSetAttribute(k_pop_staged<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-            attr_done = true;
-        }
-        k_pop_staged<NB><<<grid, BW * 32, SMEM, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, shared_tables);
-    } else {
-        k_pop_full<NB><<<grid, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, shared_tables);
-    }
+    k_pop_full<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pfull, coarse, fix, sym, L, bits, shared_tables);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
 }
@@ -606,44 +453,34 @@ int launch_pop_full(bsw_streams *s, int first, int count, const uint32_t *pfull,
 template <int NB>
 int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
                 int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int bits, int q, void *scratch,
-                size_t scratch_bytes, cudaStream_t st) {
-    constexpr int S = 32 * NB;
+                cudaStream_t st) {
     dim3 grid((unsigned)L, (count + RW - 1) / RW);
-    // pop scratch layout: [full table: count*L*S u32 (only if it fits)] [coarse: count*L*NB u32] [fix: count*L uint2]
-    const size_t full_bytes = (size_t)count * L * S * 4, small_bytes = (size_t)count * L * NB * 4 + (size_t)count * L * 8;
-    const bool full = pop && NB >= 4 && scratch_bytes >= full_bytes + small_bytes;
+    // pop scratch layout: [coarse: count*L*NB u32, rounded up to 8 bytes] [fix: count*L uint2]
     uint4 *pairs = (uint4 *)scratch;
-    uint32_t *pfull = full ? (uint32_t *)scratch : nullptr;
-    uint32_t *coarse = (uint32_t *)((uint8_t *)scratch + (full ? full_bytes : 0));
-    uint2 *fix = (uint2 *)((uint8_t *)coarse + (size_t)count * L * NB * 4);
-    // Endpoint-row staging: plain coalesced loads into a conflict-free padded tile (default), or 32 TMA bulk copies
-    // completing on an mbarrier (BSW_ROWS_TMA=1).  Measured on B200, C8, 1024 streams: 4.53 ms vs 5.40 ms per z level --
-    // 256-byte bulk copies are too small to beat two in-flight loads per thread, so TMA staging is the documented option,
-    // not the default.
+    uint32_t *coarse = (uint32_t *)scratch;
+    uint2 *fix = (uint2 *)((uint8_t *)scratch + (((size_t)count * L * NB * 4 + 7) & ~(size_t)7));
     const BswApxRegs kp = bsw_apx_params();
-    static const bool tma = getenv("BSW_ROWS_TMA") && getenv("BSW_ROWS_TMA")[0] == '1';
     // BSW_ROWS_EXACT=1: evaluate the exact cdf for every bin instead of screening with bsw_cdf_apx (A/B switch; same output)
-    static const bool exact = tma || bits > 31 || (getenv("BSW_ROWS_EXACT") && getenv("BSW_ROWS_EXACT")[0] == '1');
+    static const bool env_exact = getenv("BSW_ROWS_EXACT") && getenv("BSW_ROWS_EXACT")[0] == '1';
+    const bool exact = bits > 31 || env_exact;
     if (phase == 0) {
-#define BSW_ROWS_LAUNCH(POP_, TMA_, APX_, FULL_)                                                                              \
-    k_rows<NB, POP_, TMA_, APX_, FULL_><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, POP_ ? nullptr : sym, bits, q, \
-                                                                  POP_ ? nullptr : pairs, POP_ ? coarse : nullptr,            \
-                                                                  POP_ ? fix : nullptr, POP_ ? pfull : nullptr, kp)
         if (pop) {
-            if (tma) { if (full) BSW_ROWS_LAUNCH(true, true, false, true); else BSW_ROWS_LAUNCH(true, true, false, false); }
-            else if (exact) { if (full) BSW_ROWS_LAUNCH(true, false, false, true); else BSW_ROWS_LAUNCH(true, false, false, false); }
-            else { if (full) BSW_ROWS_LAUNCH(true, false, true, true); else BSW_ROWS_LAUNCH(true, false, true, false); }
+            if (exact) k_rows<NB, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, kp);
+            else k_rows<NB, true, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, kp);
         } else {
-            if (tma) BSW_ROWS_LAUNCH(false, true, false, false);
-            else if (exact) BSW_ROWS_LAUNCH(false, false, false, false);
-            else BSW_ROWS_LAUNCH(false, false, true, false);
+            if (exact) k_rows<NB, false, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, kp);
+            else k_rows<NB, false, true><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, sym, bits, q, pairs, nullptr, nullptr, kp);
         }
-#undef BSW_ROWS_LAUNCH
     } else {
-        if (pop && full) return launch_pop_full<NB>(s, first, count, pfull, coarse, fix, sym, L, bits, 0, st);
-        else if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
+        if (pop) k_pop_coarse<NB><<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, coarse, fix, sym, L, bits, q);
         else k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, pairs, L, bits);
     }
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+
+int launch_push_pairs(bsw_streams *s, int first, int count, const void *scratch, int64_t L, int bits, cudaStream_t st) {
+    k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, (const uint4 *)scratch, L, bits);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
 }
@@ -679,32 +516,39 @@ int bsw_pop_shared_table(bsw_streams *s, int first, int count, const uint32_t *P
     return BSW_E_INVALID;
 }
 
-// Scratch bytes for the two-phase coder for `count` streams of L rows with support S: `full` adds room for the whole
-// integer pmf table, which lets the serial pop phase skip its float64 recomputation (used when it fits the budget).
-size_t bsw_rows_scratch_bytes(int count, int64_t L, int S, bool full) {
-    size_t small = (size_t)count * L * (S / 32) * 4 + (size_t)count * L * 8;
-    size_t push = (size_t)count * L * 16;
-    size_t pop = small + (full ? (size_t)count * L * S * 4 : 0);
-    return pop > push ? pop : push;
-}
+// ans_rows6.cu
+int bsw_rows6_build_meta(const double *endp, int64_t ers, int64_t L, int S, void *meta_dev, int *n_affine_host, cudaStream_t st);
+int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
+                     int64_t sss, const double *endp, int64_t ers, const void *meta, int16_t *sym, int64_t L, int S, int bits,
+                     int q, void *scratch, size_t scratch_bytes, cudaStream_t st);
+
+// Scratch bytes of the two-phase coder for `count` streams of L rows: per row 16 B (push: P, C, reciprocal) or
+// 136 B (pop: 32 chunk bases + argmax/remnant), whichever kernel family runs.
+size_t bsw_rows_scratch_bytes(int count, int64_t L) { return (size_t)count * L * 136; }
 
 // Two-phase variants of bsw_logistic_push / bsw_logistic_pop (same arguments + caller-provided scratch).
 // phase 0 = the parallel row-table kernel, phase 1 = the serial coder; call both, in order, on one stream, with the
-// same scratch and scratch_bytes (the pop path picks the full-table variant when the scratch is large enough).
+// same scratch.  meta != NULL selects the affine-row kernels of ans_rows6.cu (meta = bsw_rows6_build_meta of these
+// endpoint rows); meta == NULL the generic ones above.
 int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
-                    int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
-                    void *scratch, size_t scratch_bytes, cudaStream_t st) {
+                    int64_t sss, const double *endp, int64_t ers, const void *meta, int16_t *sym, int64_t L, int S, int bits,
+                    int q, void *scratch, size_t scratch_bytes, cudaStream_t st) {
     BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B, "stream range out of bounds");
     BSW_REQUIRE(mu && sc && endp && sym && scratch && L > 0 && L < 65536 * 32, "two-phase coder: bad arguments");
     BSW_REQUIRE(ers == 0 || ers >= S, "two-phase coder: endpoint rows must hold S doubles (+1e300 padded)");
-    BSW_REQUIRE(scratch_bytes >= bsw_rows_scratch_bytes(count, L, S, false), "two-phase coder: scratch too small");
+    BSW_REQUIRE(scratch_bytes >= bsw_rows_scratch_bytes(count, L), "two-phase coder: scratch too small");
+    BSW_REQUIRE((((uintptr_t)scratch) & 15) == 0, "two-phase coder: scratch must be 16-byte aligned");
+    if (meta) {
+        if (phase == 1 && !pop) return launch_push_pairs(s, first, count, scratch, L, bits, st);
+        return bsw_rows6_launch(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, meta, sym, L, S, bits, q, scratch, scratch_bytes, st);
+    }
     switch (S) {
-        case 32:   return launch_rows<1>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
-        case 64:   return launch_rows<2>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
-        case 128:  return launch_rows<4>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
-        case 256:  return launch_rows<8>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
-        case 512:  return launch_rows<16>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
-        case 1024: return launch_rows<32>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, scratch_bytes, st);
+        case 32:   return launch_rows<1>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 64:   return launch_rows<2>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 128:  return launch_rows<4>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 256:  return launch_rows<8>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 512:  return launch_rows<16>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
+        case 1024: return launch_rows<32>(phase, pop, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, bits, q, scratch, st);
     }
     bsw_set_error("two-phase coder: support must be one of 32,64,...,1024 (got %d)", S);
     return BSW_E_INVALID;
@@ -824,27 +668,44 @@ extern "C" int bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_ho
     return BSW_OK;
 }
 
-extern "C" int bsw_set_pop_staged(int on) { g_pop_staged = on < 0 ? -1 : (on ? 1 : 0); return BSW_OK; }
-
 // ---- C ABI of the two-phase coder (same contract as bsw_logistic_push/pop + caller-provided scratch) -----------------
+// Kernel family for these two entry points: -1 (default) = look at the endpoint rows (one small kernel + a stream
+// synchronise) and use the affine-row kernels when every row is a uniform grid, the generic ones otherwise; 0 = generic;
+// 1 = affine kernels regardless (rows that are not uniform grids then take their exact path for every bin: correct, slow).
+// The codec does not pay the probe: bsw_bins_create classifies every level once.
+static int g_rows_mode = -1;
+extern "C" int bsw_set_rows_mode(int mode) { g_rows_mode = mode < 0 ? -1 : (mode > 1 ? 1 : mode); return BSW_OK; }
+int bsw_rows_mode() {
+    static const int env = getenv("BSW_ROWS_MODE") ? atoi(getenv("BSW_ROWS_MODE")) : -1;
+    return g_rows_mode >= 0 ? g_rows_mode : (env >= 0 && env <= 1 ? env : -1);
+}
 extern "C" int64_t bsw_logistic_scratch_bytes(int count, int64_t L, int S, int full_tables) {
-    return (int64_t)bsw_rows_scratch_bytes(count, L, S, full_tables != 0);
+    (void)S; (void)full_tables;                           // (the full-table variant of round 1 is gone: same size for every S)
+    return (int64_t)(((bsw_rows_scratch_bytes(count, L) + 63) & ~(size_t)63) + (size_t)L * 32 + 64);   // + room for the row metadata
+}
+static int abi_2p(bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc, int64_t sss,
+                  const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q, void *scratch,
+                  int64_t scratch_bytes, cudaStream_t st) {
+    BSW_REQUIRE(scratch && scratch_bytes >= bsw_logistic_scratch_bytes(count, L, S, 0), "two-phase coder: scratch too small");
+    const void *meta = nullptr;
+    const int mode = bsw_rows_mode();
+    if (mode != 0 && S >= 8 && bits >= 8 && bits <= 31) {
+        void *m = (uint8_t *)scratch + ((bsw_rows_scratch_bytes(count, L) + 63) & ~(size_t)63);
+        int n_aff = 0;
+        if (int rc = bsw_rows6_build_meta(endp, ers, L, S, m, &n_aff, st)) return rc;
+        if (mode == 1 || n_aff == (ers == 0 ? 1 : (int)L)) meta = m;
+    }
+    const size_t sb = bsw_rows_scratch_bytes(count, L);
+    if (int rc = bsw_logistic_2p(0, pop, s, first, count, mu, mss, sc, sss, endp, ers, meta, sym, L, S, bits, q, scratch, sb, st)) return rc;
+    return bsw_logistic_2p(1, pop, s, first, count, mu, mss, sc, sss, endp, ers, meta, sym, L, S, bits, q, scratch, sb, st);
 }
 extern "C" int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc, int64_t sss,
                                     const double *endp, int64_t ers, const int16_t *sym, int64_t L, int S, int bits, int q,
                                     void *scratch, int64_t scratch_bytes, void *stream) {
-    int rc = bsw_logistic_2p(0, false, s, first, count, mu, mss, sc, sss, endp, ers, (int16_t *)sym, L, S, bits, q, scratch,
-                             (size_t)scratch_bytes, (cudaStream_t)stream);
-    if (rc) return rc;
-    return bsw_logistic_2p(1, false, s, first, count, mu, mss, sc, sss, endp, ers, (int16_t *)sym, L, S, bits, q, scratch,
-                           (size_t)scratch_bytes, (cudaStream_t)stream);
+    return abi_2p(false, s, first, count, mu, mss, sc, sss, endp, ers, (int16_t *)sym, L, S, bits, q, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 extern "C" int bsw_logistic_pop_2p(bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc, int64_t sss,
                                    const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
                                    void *scratch, int64_t scratch_bytes, void *stream) {
-    int rc = bsw_logistic_2p(0, true, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, S, bits, q, scratch,
-                             (size_t)scratch_bytes, (cudaStream_t)stream);
-    if (rc) return rc;
-    return bsw_logistic_2p(1, true, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, S, bits, q, scratch,
-                           (size_t)scratch_bytes, (cudaStream_t)stream);
+    return abi_2p(true, s, first, count, mu, mss, sc, sss, endp, ers, sym, L, S, bits, q, scratch, scratch_bytes, (cudaStream_t)stream);
 }

@@ -40,12 +40,13 @@ int bsw_ans_push_i16(bsw_streams *s, int first, int count, const uint32_t *P, co
 int bsw_ans_pop_i16(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *C, int64_t pss, int64_t css,
                     int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
 
-size_t bsw_rows_scratch_bytes(int count, int64_t L, int S, bool full);
+size_t bsw_rows_scratch_bytes(int count, int64_t L);
+int bsw_rows_mode();
 int bsw_prior_coarse(const uint32_t *C, int64_t L, int S, uint32_t *coarse, uint2 *fix, cudaStream_t st);
 int bsw_pop_shared_table(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *coarse, const uint2 *fix,
                          int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
 int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, const float *mu, int64_t mss, const float *sc,
-                    int64_t sss, const double *endp, int64_t ers, int16_t *sym, int64_t L, int S, int bits, int q,
+                    int64_t sss, const double *endp, int64_t ers, const void *meta, int16_t *sym, int64_t L, int S, int bits, int q,
                     void *scratch, size_t scratch_bytes, cudaStream_t st);
 
 __global__ void k_u8_to_i16(const uint8_t *__restrict__ in, int16_t *__restrict__ out, int64_t n) {
@@ -74,13 +75,8 @@ extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int 
     BSW_CUDA(cudaMalloc(&c->xsym, sizeof(int16_t) * c->xdim * max_batch));
     c->zs.assign(c->nz, nullptr);
     {
-        // room for the full integer tables when that stays under FULL_BUDGET (small batches / pipelined lanes): the serial
-        // pop phase then needs no float64 recomputation
-        const size_t FULL_BUDGET = (size_t)3 << 30;
-        size_t a = bsw_rows_scratch_bytes(max_batch, c->zdim, c->S, false), b2 = bsw_rows_scratch_bytes(max_batch, c->xdim, 256, false);
-        size_t af = bsw_rows_scratch_bytes(max_batch, c->zdim, c->S, true), bf = bsw_rows_scratch_bytes(max_batch, c->xdim, 256, true);
-        size_t small = a > b2 ? a : b2, big = af > bf ? af : bf;
-        c->scratch_bytes = big <= FULL_BUDGET ? big : small;
+        size_t a = bsw_rows_scratch_bytes(max_batch, c->zdim), b2 = bsw_rows_scratch_bytes(max_batch, c->xdim);
+        c->scratch_bytes = a > b2 ? a : b2;
         BSW_CUDA(cudaMalloc(&c->scratch, c->scratch_bytes));
         c->two_phase = 1;
     }
@@ -176,6 +172,11 @@ struct Ctx {
     void coder_stream() { if (c->dual_stream == 1) use(c->st_lo); else if (c->dual_stream == 2) use(caller); }
     void serial_stream() { if (c->dual_stream == 2) use(c->st_hi); }
     const double *zend(int lvl) const { return c->b->zend + (size_t)lvl * c->zdim * c->S; }
+    // row metadata of a level whose rows are all uniform grids (-> affine-row kernels), else NULL (-> generic kernels)
+    const void *zmeta(int lvl) const {
+        return (c->b->zaffine[lvl] && bsw_rows_mode() != 0) ? (const uint8_t *)c->b->zmeta + (size_t)32 * lvl * c->zdim : nullptr;
+    }
+    const void *xmeta() const { return (c->b->xaffine && bsw_rows_mode() != 0) ? c->b->xmeta : nullptr; }
     int infer(int zi) { conv_stream(); return bsw_model_run(c->m, true, zi, c->given, count, c->mu, c->scale, 1, st, &nl, &c->prof); }
     int generate(int zi) { conv_stream(); return bsw_model_run(c->m, false, zi, c->given, count, c->mu, c->scale, 0, st, &nl, &c->prof); }
     int gather_x(const uint8_t *x) {
@@ -207,12 +208,12 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_Z, st);
-        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
+        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, zmeta(lvl), (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         serial_stream();
         c->prof.begin(CAT_POP_Z, st);
-        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
+        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, zmeta(lvl), (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }
@@ -227,12 +228,12 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_Z, st);
-        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
+        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, zmeta(lvl), (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         serial_stream();
         c->prof.begin(CAT_PUSH_Z, st);
-        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
+        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->zdim, c->scale, c->zdim, zend(lvl), c->S, zmeta(lvl), (int16_t *)sym, c->zdim, c->S, 31, c->q, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }
@@ -249,12 +250,12 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_X, st);
-        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
+        int rc = bsw_logistic_2p(0, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, xmeta(), (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         serial_stream();
         c->prof.begin(CAT_POP_X, st);
-        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
+        rc = bsw_logistic_2p(1, true, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, xmeta(), (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }
@@ -269,12 +270,12 @@ struct Ctx {
         }
         nl += 2;
         c->prof.begin(CAT_ROWS_X, st);
-        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
+        int rc = bsw_logistic_2p(0, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, xmeta(), (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         if (rc) return rc;
         serial_stream();
         c->prof.begin(CAT_PUSH_X, st);
-        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
+        rc = bsw_logistic_2p(1, false, s, first, count, c->mu, c->xdim, c->scale, xss(), c->b->xend, 0, xmeta(), (int16_t *)sym, c->xdim, 256, 31, 8, c->scratch, c->scratch_bytes, st);
         c->prof.end(st);
         return rc;
     }

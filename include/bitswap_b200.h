@@ -53,6 +53,7 @@ int         bsw_selftest_cdf_apx(int64_t n, uint64_t seed, double *worst_units_h
  * list, export == reading it back / pickle.dump (cifar_compress.py:265-266).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct bsw_streams bsw_streams;
+typedef struct bsw_bins bsw_bins;
 
 /* capacity_words is rounded up to a multiple of 32. */
 int bsw_streams_create(bsw_streams **out, int n_streams, int64_t capacity_words);
@@ -149,13 +150,23 @@ int bsw_logistic_pop(bsw_streams *s, int first, int count, const float *mu_dev, 
                      int quantbits, void *stream);
 
 /* Two-phase variants (the throughput path of the codec): a fully parallel float64 row-table kernel followed by the
- * serial integer coder; same arguments and bit-identical results, plus caller-provided device scratch of at least
- * bsw_logistic_scratch_bytes(count, L, S, 0) bytes.  With bsw_logistic_scratch_bytes(count, L, S, 1) bytes the pop
- * keeps the whole integer table of the level and its serial phase needs no float64 work (small batches). */
+ * serial integer coder; same arguments and bit-identical results, plus caller-provided 16-byte aligned device scratch
+ * of at least bsw_logistic_scratch_bytes(count, L, S, 0) bytes (the last argument is ignored; kept for ABI stability).
+ * Two kernel families: the generic one (any sorted endpoint rows) and the affine-row one for rows that are uniform
+ * grids -- which is every row discretize_kbins() builds (discretization.py:105-118) and the ImageBins pixel row
+ * (utils/torch/rand.py:146-147).  These two entry points probe the rows on every call (one small kernel + a stream
+ * synchronise); the codec uses the classification bsw_bins_create made. */
 int64_t bsw_logistic_scratch_bytes(int count, int64_t L, int S, int full_tables);
-/* Full-table pops: 1 = serial phase with rows staged through shared memory by bulk copies (shorter critical path, reads the
- * whole table), 0 = dependent 128-byte loads (default), -1 = let the BSW_POP_STAGED environment variable decide. */
-int bsw_set_pop_staged(int on);
+/* Kernel family for bsw_logistic_*_2p and the codec: -1 = by row classification (default; BSW_ROWS_MODE overrides),
+ * 0 = generic kernels only, 1 = affine-row kernels for every row (non-uniform rows take the exact path per bin). */
+int bsw_set_rows_mode(int mode);
+/* 1 if every endpoint row of `level` (or the pixel row, level = -1) is a uniform grid. */
+int bsw_bins_level_is_uniform(const bsw_bins *b, int level);
+/* Debug: with verify on, every affine-row table launch also evaluates the exact function for every bin.
+ * bsw_rows6_verify_read returns and resets {bins that differ from the exact function (must be 0), worst error of a
+ * trusted bin in thousandths of its window, bins checked, bins that took the exact path}. */
+int bsw_rows6_set_verify(int on);
+int bsw_rows6_verify_read(uint64_t *out4_host);
 int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
                          const float *scale_dev, int64_t scale_stream_stride, const double *endpoints_dev,
                          int64_t endp_row_stride, const int16_t *sym_dev, int64_t L, int S, int bits, int quantbits,
@@ -171,7 +182,6 @@ int bsw_logistic_pop_2p(bsw_streams *s, int first, int count, const float *mu_de
  * (utils/torch/rand.py:134-153); the library keeps its own padded copy (each endpoint row padded
  * with +1e300 to S entries so that cdf_{S-1} == 1 falls out of the same formula).
  * ---------------------------------------------------------------------------------------------- */
-typedef struct bsw_bins bsw_bins;
 /* zendpoints_host [nz, zdim, S-1], zcentres_host [nz, zdim, S] float64 (reference layout). */
 int bsw_bins_create(bsw_bins **out, int nz, int zdim, int quantbits, int xdim,
                     const double *zendpoints_host, const double *zcentres_host);

@@ -315,14 +315,15 @@ def _pad_big(ends):
     return out
 
 
-@pytest.mark.parametrize("S,q,full", [(1024, 10, 0), (1024, 10, 1), (1024, 10, 2), (256, 8, 1), (256, 8, 2), (128, 7, 0), (128, 7, 2),
-                                      (64, 6, 0), (32, 5, 0)])
-def test_two_phase_abi_extreme_tables_vs_fused_and_oracle(S, q, full):
+@pytest.mark.parametrize("S,q,mode", [(1024, 10, 0), (1024, 10, -1), (1024, 10, 1), (256, 8, 0), (256, 8, -1), (128, 7, -1), (128, 7, 0),
+                                      (64, 6, 0), (64, 6, -1), (32, 5, 0), (32, 5, -1)])
+def test_two_phase_abi_extreme_tables_vs_fused_and_oracle(S, q, mode):
     """Two-phase coder through the C ABI against the fused kernels and the oracle (fed our exact pmfs), on hostile rows:
     sigma at the x-level minimum (2/255/8) so that almost every bin is a saturated tail (P = 1, huge remnant), means far
-    outside the bin range, symbols in the dead tails, plus ordinary rows."""
-    staged, full = int(full == 2), int(full > 0)         # full == 2: full tables + the bulk-copy staged serial phase
-    check(lib().bsw_set_pop_staged(staged))
+    outside the bin range, symbols in the dead tails, plus ordinary rows.  mode 0 = generic kernels (k_rows/k_pop_coarse),
+    -1 = classify the rows (uniform grids here -> the affine-row kernels k_rows6/k_pop6), 1 = affine kernels forced."""
+    check(lib().bsw_set_rows_mode(mode))
+    full = 0
     rs = np.random.RandomState(S + full)
     B, L = 9, 96
     lo, hi = -6 - rs.uniform(0, 1, L), 6 + rs.uniform(0, 1, L)
@@ -371,7 +372,7 @@ def test_two_phase_abi_extreme_tables_vs_fused_and_oracle(S, q, full):
                                           L, S, 31, q, cuda_stream_ptr()))
         ss.raise_on_error()
         res[name] = (after_pop, popped, ss.export_lists())
-    check(lib().bsw_set_pop_staged(-1))
+    check(lib().bsw_set_rows_mode(-1))
     assert res["2p"][0] == res["fused"][0] and np.array_equal(res["2p"][1], res["fused"][1]) and res["2p"][2] == res["fused"][2]
     for b in range(B):
         a = O.AnsC(tables=tabs[b])
@@ -388,3 +389,86 @@ def test_screening_cdf_error_is_far_inside_the_window():
     check(lib().bsw_selftest_cdf_apx(1 << 27, 777, ctypes.byref(worst)))
     print("worst |apx - exact| =", worst.value, "units of 2^-51")
     assert worst.value < 8.0
+
+
+def _level_case(L, S, q, B, seed, affine=True, sc_lo=0.1):
+    rs = np.random.RandomState(seed)
+    if affine:
+        lo, hi = -6 - rs.uniform(0, 1, L), 6 + rs.uniform(0, 1, L)
+        ends = np.linspace(lo, hi, S + 1, axis=1)[:, 1:-1].copy()
+    else:                                                   # the top level: equal-mass logistic bins, float32 (discretization.py:25-27)
+        from bitswap_b200.rand import Bins
+        ends = Bins(torch.zeros((1, 1, L)), torch.ones((1, 1, L)), q).endpoints().numpy().reshape(L, S - 1).astype(np.float64)
+    mu = rs.normal(0, 1.5, (B, L)).astype(np.float32)
+    sc = rs.uniform(sc_lo, 1.0, (B, L)).astype(np.float32)
+    return ends, mu, sc
+
+
+def _run_2p(ends, mu, sc, S, q, states, sym, mode):
+    """pop then push of one level through the two-phase ABI; returns (states after pop, popped symbols, states after push)."""
+    B, L = mu.shape
+    check(lib().bsw_set_rows_mode(mode))
+    e_pad = torch.from_numpy(_pad_big(ends)).to(dev)
+    dmu, dsc, dsym = torch.from_numpy(mu).to(dev), torch.from_numpy(sc).to(dev), torch.from_numpy(sym).to(dev)
+    nbytes = int(lib().bsw_logistic_scratch_bytes(B, L, S, 0))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ss = StreamSet(B, 1 << 14)
+    ss.import_lists(states)
+    out = torch.zeros((B, L), dtype=torch.int16, device=dev)
+    check(lib().bsw_logistic_pop_2p(ss.handle, 0, B, dmu.data_ptr(), L, dsc.data_ptr(), L, e_pad.data_ptr(), S, out.data_ptr(),
+                                    L, S, 31, q, scratch.data_ptr(), nbytes, cuda_stream_ptr()))
+    ss.raise_on_error()
+    a, popped = ss.export_lists(), out.cpu().numpy().copy()
+    check(lib().bsw_logistic_push_2p(ss.handle, 0, B, dmu.data_ptr(), L, dsc.data_ptr(), L, e_pad.data_ptr(), S, dsym.data_ptr(),
+                                     L, S, 31, q, scratch.data_ptr(), nbytes, cuda_stream_ptr()))
+    ss.raise_on_error()
+    check(lib().bsw_set_rows_mode(-1))
+    return a, popped, ss.export_lists()
+
+
+def test_affine_rows_full_size_level_every_bin_verified_against_the_exact_function():
+    """the screened table kernels are sound only if every integer they emit is the exact function's.
+    A full-size latent level (2048 rows x 1024 bins, q = 10, sigma down to the 0.1 floor) is run through k_rows6 in
+    verify mode, which evaluates the exact function (bsw_cdf_fast on the real endpoints) for EVERY bin next to the
+    screened value: 0 disagreements, the worst screening error of a trusted bin below a quarter of its window, and the
+    streams equal what the generic kernels leave."""
+    L, S, q, B = 2048, 1024, 10, 16
+    ends, mu, sc = _level_case(L, S, q, B, seed=3)
+    sc[:, ::7] = np.float32(0.1)
+    mu[:, ::11] *= 3
+    rs = np.random.RandomState(5)
+    sym = rs.randint(0, S, size=(B, L)).astype(np.int16)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(6000 + b, seed=700 + b)
+        states.append([int(v) for v in w] + [head])
+    check(lib().bsw_rows6_set_verify(1))
+    stats = np.zeros(4, dtype=np.uint64)
+    try:
+        got = _run_2p(ends, mu, sc, S, q, states, sym, mode=-1)
+        check(lib().bsw_rows6_verify_read(stats.ctypes.data))
+    finally:
+        check(lib().bsw_rows6_set_verify(0))
+    mism, worst, checked, exact_path = (int(v) for v in stats)
+    print(f"verify: {checked} bins evaluated of {2 * B * L * S}, {exact_path} took the exact path, worst trusted error "
+          f"{worst / 10:.1f} % of the window, {mism} mismatches")
+    assert checked > 0.25 * 2 * B * L * S and mism == 0
+    assert worst <= 250, worst                            # a trusted bin's error must stay below a quarter of its window
+    ref = _run_2p(ends, mu, sc, S, q, states, sym, mode=0)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+
+
+def test_affine_kernels_forced_on_non_uniform_rows_fall_back_to_the_exact_function():
+    """mode 1 pushes the equal-mass top-level rows (not a uniform grid) through k_rows6/k_pop6: the plan refuses to
+    vouch for them (mask = 0) and every bin takes the exact path -- same streams as the generic kernels."""
+    L, S, q, B = 96, 1024, 10, 5
+    ends, mu, sc = _level_case(L, S, q, B, seed=9, affine=False)
+    sym = np.random.RandomState(1).randint(0, S, size=(B, L)).astype(np.int16)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(3000 + b, seed=800 + b)
+        states.append([int(v) for v in w] + [head])
+    a = _run_2p(ends, mu, sc, S, q, states, sym, mode=1)
+    b = _run_2p(ends, mu, sc, S, q, states, sym, mode=0)
+    c = _run_2p(ends, mu, sc, S, q, states, sym, mode=-1)       # classification -> generic
+    assert a[0] == b[0] == c[0] and np.array_equal(a[1], b[1]) and a[2] == b[2] == c[2]
