@@ -154,6 +154,26 @@ EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure
            "bsw_codec_encode", "bsw_codec_decode", "bsw_codec_last_launches", "bsw_codec_profile", "bsw_codec_set_two_phase", "bsw_codec_set_dual_stream"]
 
 
+def device_index(device=None):
+    """CUDA device ordinal of `device` (torch.device / "cuda:N" / int / None = the current device)."""
+    import torch
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise BswError(f"bitswap_b200 needs a CUDA device, got {device!r} (there is no CPU fallback)")
+    return torch.cuda.current_device() if d.index is None else d.index
+
+
+def on_device(index):
+    """Context manager: every library object allocates and launches on the device it was created for, whatever the
+    caller's current device is (the reference scripts pass device=f"cuda:{gpu}" without ever calling set_device)."""
+    import torch
+    return torch.cuda.device(index)
+
+
 def cuda_stream_ptr():
     """torch's current CUDA stream as a void* for the `stream` argument of the C ABI."""
     import torch

@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import lib, check, cuda_stream_ptr
+from ._lib import lib, check, cuda_stream_ptr, device_index, on_device
 from .config import CodecConfig
 from .model import Model
 from .streams import StreamSet
@@ -22,12 +22,18 @@ class Bins:
     """Device copy of the discretisation tables (zendpoints [nz,zdim,2^q-1], zcentres [nz,zdim,2^q],
     the layout discretize() returns, discretization.py:99)."""
 
-    def __init__(self, cfg: CodecConfig, zendpoints, zcentres):
+    def __init__(self, cfg: CodecConfig, zendpoints, zcentres, device=None):
+        self.device = device_index(device)
         ze = np.ascontiguousarray(zendpoints.detach().cpu().numpy() if torch.is_tensor(zendpoints) else zendpoints, dtype=np.float64)
         zc = np.ascontiguousarray(zcentres.detach().cpu().numpy() if torch.is_tensor(zcentres) else zcentres, dtype=np.float64)
         assert ze.shape == (cfg.nz, cfg.zdim, cfg.zsupport - 1) and zc.shape == (cfg.nz, cfg.zdim, cfg.zsupport)
         self._h = ctypes.c_void_p()
-        check(lib().bsw_bins_create(ctypes.byref(self._h), cfg.nz, cfg.zdim, cfg.quantbits, cfg.xdim, ze.ctypes.data, zc.ctypes.data))
+        with on_device(self.device):
+            check(lib().bsw_bins_create(ctypes.byref(self._h), cfg.nz, cfg.zdim, cfg.quantbits, cfg.xdim, ze.ctypes.data, zc.ctypes.data))
+
+    def level_is_uniform(self, level):
+        """True if every endpoint row of latent level `level` (-1: the pixel row) is a uniform grid (affine-row kernels)."""
+        return bool(lib().bsw_bins_level_is_uniform(self._h, int(level)))
 
     @property
     def handle(self):
@@ -46,8 +52,12 @@ class Bins:
 class BitSwapCodec:
     def __init__(self, cfg: CodecConfig, model: Model, bins: Bins, max_batch: int):
         self.cfg, self.model, self.bins, self.max_batch = cfg, model, bins, int(max_batch)
+        self.device = model.device
+        if bins.device != self.device:
+            raise ValueError(f"model is on cuda:{model.device} but the bin tables are on cuda:{bins.device}")
         self._h = ctypes.c_void_p()
-        check(lib().bsw_codec_create(ctypes.byref(self._h), model.handle, bins.handle, self.max_batch))
+        with on_device(self.device):
+            check(lib().bsw_codec_create(ctypes.byref(self._h), model.handle, bins.handle, self.max_batch))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -61,14 +71,23 @@ class BitSwapCodec:
     def encode(self, streams: StreamSet, x: torch.Tensor, first=0, scheme=BITSWAP):
         """x: uint8 CUDA tensor [count, C, 32, 32]; pushes one image onto each of `count` streams. Async."""
         assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()
+        self._same_device(streams, x)
         count = x.shape[0]
-        check(lib().bsw_codec_encode(self._h, streams.handle, first, count, x.data_ptr(), scheme, cuda_stream_ptr()))
+        with on_device(self.device):
+            check(lib().bsw_codec_encode(self._h, streams.handle, first, count, x.data_ptr(), scheme, cuda_stream_ptr()))
+
+    def _same_device(self, streams, x=None):
+        if streams.device != self.device or (x is not None and x.device.index != self.device):
+            raise ValueError(f"codec is on cuda:{self.device}; streams on cuda:{streams.device}"
+                             + (f", pixels on {x.device}" if x is not None else ""))
 
     def decode(self, streams: StreamSet, count: int, first=0, scheme=BITSWAP, out=None):
         """Pops one image from each stream; returns uint8 CUDA tensor [count, C, 32, 32]. Async."""
         if out is None:
-            out = torch.empty((count,) + tuple(self.cfg.xs), dtype=torch.uint8, device="cuda")
-        check(lib().bsw_codec_decode(self._h, streams.handle, first, count, out.data_ptr(), scheme, cuda_stream_ptr()))
+            out = torch.empty((count,) + tuple(self.cfg.xs), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        self._same_device(streams, out)
+        with on_device(self.device):
+            check(lib().bsw_codec_decode(self._h, streams.handle, first, count, out.data_ptr(), scheme, cuda_stream_ptr()))
         return out
 
     @property
@@ -106,6 +125,7 @@ class PipelinedCodec:
 
     def __init__(self, cfg: CodecConfig, state_dict, bins: Bins, max_batch: int, lanes: int = 4, use_tensor_cores=True, lane_size: int = 0):
         self.cfg, self.bins, self.max_batch = cfg, bins, int(max_batch)
+        self.device = bins.device
         self.lanes = max(1, min(int(lanes), self.max_batch))
         self.per = -(-self.max_batch // self.lanes)
         if lane_size > 0:             # explicit sub-batch size (the last lane takes the remainder), e.g. a multiple of SMs/2
@@ -114,11 +134,11 @@ class PipelinedCodec:
         self.models, self.codecs, self.streams = [], [], []
         self.serial = False          # True: run the lanes back to back on the current stream (clean per-kernel timing)
         for _ in range(self.lanes):
-            m = Model.from_config(cfg, max_batch=self.per, use_tensor_cores=use_tensor_cores).load_state_dict(state_dict)
+            m = Model.from_config(cfg, max_batch=self.per, use_tensor_cores=use_tensor_cores, device=self.device).load_state_dict(state_dict)
             m.compress()
             self.models.append(m)
             self.codecs.append(BitSwapCodec(cfg, m, bins, self.per))
-            self.streams.append(torch.cuda.Stream())
+            self.streams.append(torch.cuda.Stream(device=self.device))
 
     def _ranges(self, count):
         out, b = [], 0
@@ -132,7 +152,7 @@ class PipelinedCodec:
             for i, (b, n) in enumerate(self._ranges(count)):
                 fn(self.codecs[i], b, n)
             return
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(cur)
         for i, (b, n) in enumerate(self._ranges(count)):
@@ -149,7 +169,7 @@ class PipelinedCodec:
 
     def decode(self, streams: StreamSet, count: int, first=0, scheme=BITSWAP, out=None):
         if out is None:
-            out = torch.empty((count,) + tuple(self.cfg.xs), dtype=torch.uint8, device="cuda")
+            out = torch.empty((count,) + tuple(self.cfg.xs), dtype=torch.uint8, device=torch.device("cuda", self.device))
         self._fan(count, lambda c, b, n: c.decode(streams, n, first=first + b, scheme=scheme, out=out[b:b + n]))
         return out
 

@@ -456,12 +456,17 @@ __global__ void __launch_bounds__(TW * 32) k_push_tables(bsw_streams sv, int fir
         uint32_t p = 1, c = 0;
         if (i < L) {
             int s = (int)sy[i];
-            p = Pb[i * S + s];
-            c = Cb[i * (S + 1) + s];
+            if ((unsigned)s < (unsigned)S) {
+                p = Pb[i * S + s];
+                c = Cb[i * (S + 1) + s];
+            } else p = 0;                                  // symbol outside the support: no table read; flagged below
         }
         int n = (int)min((int64_t)32, L - i0);
-        for (int j = 0; j < n && !ws.err; ++j)
-            ws.encode(__shfl_sync(FULL, p, j), __shfl_sync(FULL, c, j), bits, lane);
+        for (int j = 0; j < n && !ws.err; ++j) {
+            const uint32_t pj = __shfl_sync(FULL, p, j);
+            if (pj == 0u) { ws.err = BSW_E_INVALID; break; }   // the reference raises IndexError at self.pmfs[i, s] (:50)
+            ws.encode(pj, __shfl_sync(FULL, c, j), bits, lane);
+        }
     }
     ws.push_end(lane);
     ws.close(sv, b, lane);
@@ -737,6 +742,7 @@ __global__ void __launch_bounds__(FW * 32) k_logistic_push(bsw_streams sv, int f
         RowTable<NB> T;
         build_row<NB>(e, __shfl_sync(FULL, mu_w, j32), __shfl_sync(FULL, sc_w, j32), mult, bits, lane, T);
         int s = __shfl_sync(FULL, sym_w, j32);
+        if ((unsigned)s >= (unsigned)(32 * NB)) { ws.err = BSW_E_INVALID; break; }    // reference: IndexError at self.pmfs[i, s]
         int owner = s / NB, js = s - owner * NB;
         uint32_t acc = T.base, cs = T.base, ps = T.P[0];
 #pragma unroll

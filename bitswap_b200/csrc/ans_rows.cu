@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(RW * 32, 2) k_rows(int count, int64_t L, const
         if (lane == 0) {
             const uint32_t pf = pb + (bi == sy ? rem : 0u);
             const uint64_t M = pf == 1u ? ~0ull : ~0ull / (uint64_t)pf;      // reciprocal for the serial phase's division
-            pairs[out] = make_uint4(pf, cb + (bi < sy ? rem : 0u), (uint32_t)M, (uint32_t)(M >> 32));
+            if ((unsigned)sy >= (unsigned)S) pairs[out] = make_uint4(0u, 0u, 0u, 0u);   // out-of-range symbol: flagged by the serial phase
+            else pairs[out] = make_uint4(pf, cb + (bi < sy ? rem : 0u), (uint32_t)M, (uint32_t)(M >> 32));
         }
     }
 }
@@ -287,7 +288,9 @@ __global__ void __launch_bounds__(BW * 32) k_push_pairs(bsw_streams sv, int firs
         int n = (int)min((int64_t)32, L - i0);
         for (int j = 0; j < n && !ws.err; ++j) {
             uint64_t M = ((uint64_t)__shfl_sync(FULL, cur.w, j) << 32) | __shfl_sync(FULL, cur.z, j);
-            ws.encode_magic(__shfl_sync(FULL, cur.x, j), __shfl_sync(FULL, cur.y, j), M, bits, lane);
+            const uint32_t pj = __shfl_sync(FULL, cur.x, j);
+            if (pj == 0u) { ws.err = BSW_E_INVALID; break; }     // phase A saw a symbol outside the support (reference: IndexError)
+            ws.encode_magic(pj, __shfl_sync(FULL, cur.y, j), M, bits, lane);
         }
     }
     ws.push_end(lane);

@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
         if (lane == 0) {
             const uint32_t pf = pb + (bi == sy ? rem : 0u);
             const uint64_t Mg = pf == 1u ? ~0ull : ~0ull / (uint64_t)pf;          // reciprocal for the serial phase's division
-            pairs[out] = make_uint4(pf, cb + (bi < sy ? rem : 0u), (uint32_t)Mg, (uint32_t)(Mg >> 32));
+            if ((unsigned)sy >= (unsigned)S) pairs[out] = make_uint4(0u, 0u, 0u, 0u);    // out-of-range symbol: flagged by the serial phase
+            else pairs[out] = make_uint4(pf, cb + (bi < sy ? rem : 0u), (uint32_t)Mg, (uint32_t)(Mg >> 32));
         }
     }
 }

@@ -14,7 +14,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import lib, check, cuda_stream_ptr
+from ._lib import lib, check, cuda_stream_ptr, device_index, on_device
 from .config import CodecConfig
 from .synthetic import state_dict_spec
 
@@ -26,7 +26,7 @@ class _Desc(ctypes.Structure):
 
 class Model:
     def __init__(self, xs=(3, 32, 32), nz=1, zchannels=16, nprocessing=1, kernel_size=3, resdepth=2, reswidth=256,
-                 dropout_p=0., tag='', root_process=True, cond_xscale=False, max_batch=1, use_tensor_cores=False):
+                 dropout_p=0., tag='', root_process=True, cond_xscale=False, max_batch=1, use_tensor_cores=False, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("bitswap_b200.Model needs a CUDA device (no CPU fallback)")
         assert tuple(xs[1:]) == (32, 32), "blocks are always 32x32 (latents 16x16)"
@@ -36,11 +36,27 @@ class Model:
         self.zdim = (zchannels, 16, 16)
         self.compressing = False
         self.max_batch = int(max_batch)
-        d = _Desc(xs[0], nz, zchannels, nprocessing, kernel_size, resdepth, reswidth, int(cond_xscale), self.max_batch,
-                  int(use_tensor_cores))
+        self._desc = _Desc(xs[0], nz, zchannels, nprocessing, kernel_size, resdepth, reswidth, int(cond_xscale), self.max_batch,
+                           int(use_tensor_cores))
+        self.device = device_index(device)
         self._h = ctypes.c_void_p()
-        check(lib().bsw_model_create(ctypes.byref(self._h), ctypes.byref(d)))
+        self._sd = None
+        self._create()
+
+    def _create(self):
+        self._destroy()
+        with on_device(self.device):
+            check(lib().bsw_model_create(ctypes.byref(self._h), ctypes.byref(self._desc)))
         self._loaded = False
+
+    def _destroy(self):
+        if getattr(self, "_h", None):
+            try:
+                with on_device(self.device):
+                    lib().bsw_model_destroy(self._h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
 
     @classmethod
     def from_config(cls, cfg: CodecConfig, **kw):
@@ -49,20 +65,26 @@ class Model:
                    cond_xscale=cfg.cond_xscale, **kw)
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            try:
-                lib().bsw_model_destroy(h)
-            except Exception:
-                pass
-            self._h = None
+        self._destroy()
 
     @property
     def handle(self):
         return self._h
 
     # -- nn.Module-shaped no-ops the compression scripts call ---------------------------------------
-    def to(self, *a, **k):
+    def to(self, device=None, *a, **k):
+        """nn.Module.to(device): the handle (weights, activations) lives on ONE device; moving re-creates it there and
+        reloads the weights.  The reference scripts call Model(...).to(f"cuda:{gpu}") before load_state_dict."""
+        if device is None or isinstance(device, torch.dtype):
+            return self
+        idx = device_index(device)
+        if idx != self.device:
+            sd = self._sd
+            self._destroy()
+            self.device = idx
+            self._create()
+            if sd is not None:
+                self.load_state_dict(sd)
         return self
 
     def eval(self):
@@ -80,6 +102,15 @@ class Model:
             if missing or extra:
                 raise RuntimeError(f"state_dict mismatch: missing {missing[:4]} unexpected {extra[:4]}")
         f32 = lambda t: np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)   # noqa: E731
+        self._sd = sd
+        if self._loaded:
+            self._create()
+        with on_device(self.device):
+            self._load(sd, spec, f32)
+        self._loaded = True
+        return self
+
+    def _load(self, sd, spec, f32):
         for key, shape, kind in spec:
             if kind == "gen_std":
                 a = f32(sd[key])
@@ -93,8 +124,6 @@ class Model:
                 check(lib().bsw_model_load_conv(self._h, prefix.encode(), v.ctypes.data, g.ctypes.data, b.ctypes.data,
                                                 shape[0], shape[1], shape[2], loggain))
         check(lib().bsw_model_finalize(self._h))
-        self._loaded = True
-        return self
 
     # -- infer / generate -----------------------------------------------------------------------------
     def _run(self, infer, i, given):
@@ -105,15 +134,17 @@ class Model:
         cfg = self.cfg
         dim_in = cfg.xdim if (infer and i == 0) else cfg.zdim
         dim_out = cfg.xdim if (not infer and i == 0) else cfg.zdim
-        g = given.to(device="cuda", dtype=torch.float32).reshape(-1, dim_in).contiguous()    # h.float(), :324,:392
+        dev = torch.device("cuda", self.device)
+        g = given.to(device=dev, dtype=torch.float32).reshape(-1, dim_in).contiguous()    # h.float(), :324,:392
         n = g.shape[0]
         assert n <= self.max_batch, f"batch {n} > max_batch {self.max_batch}"
-        mu = torch.empty((n, dim_out), dtype=torch.float32, device="cuda")
-        sc = torch.empty((n, dim_out), dtype=torch.float32, device="cuda")
-        if infer:
-            check(lib().bsw_vae_infer(self._h, i, g.data_ptr(), n, mu.data_ptr(), sc.data_ptr(), cuda_stream_ptr()))
-        else:
-            check(lib().bsw_vae_generate(self._h, i, g.data_ptr(), n, mu.data_ptr(), sc.data_ptr(), 1, cuda_stream_ptr()))
+        mu = torch.empty((n, dim_out), dtype=torch.float32, device=dev)
+        sc = torch.empty((n, dim_out), dtype=torch.float32, device=dev)
+        with on_device(self.device):
+            if infer:
+                check(lib().bsw_vae_infer(self._h, i, g.data_ptr(), n, mu.data_ptr(), sc.data_ptr(), cuda_stream_ptr()))
+            else:
+                check(lib().bsw_vae_generate(self._h, i, g.data_ptr(), n, mu.data_ptr(), sc.data_ptr(), 1, cuda_stream_ptr()))
         if flat_in:
             mu, sc = mu.view(-1), sc.view(-1)
         return mu.to(in_dtype), sc.to(in_dtype)                       # .type(type), :375-376,:434-435

@@ -6,13 +6,25 @@ import ctypes
 
 import numpy as np
 
-from ._lib import lib, check
+from ._lib import lib, check, device_index, on_device
+
+
+def _on_own_device(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with on_device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 class StreamSet:
-    def __init__(self, n_streams: int, capacity_words: int):
+    def __init__(self, n_streams: int, capacity_words: int, device=None):
         self._h = ctypes.c_void_p()
-        check(lib().bsw_streams_create(ctypes.byref(self._h), int(n_streams), int(capacity_words)))
+        self.device = device_index(device)
+        with on_device(self.device):
+            check(lib().bsw_streams_create(ctypes.byref(self._h), int(n_streams), int(capacity_words)))
         self.n = int(n_streams)
         self.capacity = int(lib().bsw_streams_capacity(self._h))
 
@@ -30,11 +42,13 @@ class StreamSet:
         return self._h
 
     # -- host <-> device --------------------------------------------------------------------
+    @_on_own_device
     def fill(self, words, head):
         """Every stream := (words, head) -- the reference seeds each experiment identically."""
         w = np.ascontiguousarray(words, dtype=np.uint32)
         check(lib().bsw_streams_fill(self._h, w.ctypes.data, w.size, ctypes.c_uint64(int(head))))
 
+    @_on_own_device
     def import_lists(self, states, first=0):
         """states: iterable of reference-style lists [w0, ..., w_{n-1}, head]."""
         states = list(states)
@@ -48,6 +62,7 @@ class StreamSet:
             heads[i] = st[-1]
         check(lib().bsw_streams_import(self._h, first, len(states), words.ctypes.data, offs.ctypes.data, heads.ctypes.data))
 
+    @_on_own_device
     def import_packed(self, words, offsets, heads, first=0):
         """Inverse of export(): packed uint32 words + int64 offsets [count+1] + uint64 heads."""
         words = np.ascontiguousarray(words, dtype=np.uint32)
@@ -56,6 +71,7 @@ class StreamSet:
         wp = words.ctypes.data if words.size else None
         check(lib().bsw_streams_import(self._h, first, len(heads), wp, offsets.ctypes.data, heads.ctypes.data))
 
+    @_on_own_device
     def sizes(self):
         """(nwords int64[B], heads uint64[B], flags int32[B]) -- synchronises."""
         n = np.zeros(self.n, dtype=np.int64)
@@ -64,12 +80,14 @@ class StreamSet:
         check(lib().bsw_streams_sizes(self._h, n.ctypes.data, h.ctypes.data, f.ctypes.data))
         return n, h, f
 
+    @_on_own_device
     def min_words(self):
         """Lowest word count each stream reached since import/fill (reference: `excess_state_len - 1`)."""
         n = np.zeros(self.n, dtype=np.int64)
         check(lib().bsw_streams_min_words(self._h, n.ctypes.data))
         return n
 
+    @_on_own_device
     def export(self, first=0, count=None):
         """Packed export: (words uint32[sum], offsets int64[count+1], heads uint64[count], flags)."""
         count = self.n - first if count is None else count
@@ -82,6 +100,7 @@ class StreamSet:
         return words[:int(offs[-1])], offs, h, f
 
     # -- fast packed path: one gather/scatter kernel + three memcpys, pinned staging buffers -------------------------
+    @_on_own_device
     def _staging(self, count):
         import torch
         st = getattr(self, "_stg", None)
@@ -96,6 +115,7 @@ class StreamSet:
             self._stg = st
         return st
 
+    @_on_own_device
     def export_packed(self, first=0, count=None):
         """(words uint32[sum], offsets int64[count+1], heads uint64[count]) as numpy views of pinned host buffers
         (valid until the next export_packed/import_packed_fast).  Enqueued on torch's current stream; synchronises it."""
@@ -114,6 +134,7 @@ class StreamSet:
         return (st["words_h"][:total].numpy().view(np.uint32), st["offs_h"][:count + 1].numpy(),
                 st["heads_h"][:count].numpy().view(np.uint64))
 
+    @_on_own_device
     def import_packed_fast(self, words, offsets, heads, first=0):
         """Inverse of export_packed (host arrays -> device scatter). Async on torch's current stream."""
         import torch
@@ -141,6 +162,8 @@ class StreamSet:
         _, _, f = self.sizes()
         if (f == 1).any():
             raise IndexError(f"pop from empty ANS stack (streams {np.nonzero(f == 1)[0][:8].tolist()})")   # cifar_compress.py:65
+        if (f == 4).any():
+            raise IndexError(f"symbol outside the table's support (streams {np.nonzero(f == 4)[0][:8].tolist()})")   # P[i, s] in the reference
         if (f == 2).any():
             raise OverflowError(f"ANS word-stack capacity exhausted (streams {np.nonzero(f == 2)[0][:8].tolist()})")
         if (f != 0).any():

@@ -318,15 +318,17 @@ class ModelOracle:
 class BitSwapOracle:
     """One chain (= one reference 'experiment'): images are pushed one after
     another onto a single ANS state.  `coder` is AnsPort (list state) or AnsC
-    (CState); `pmf_fn` is logistic_pmfs_torch (reference-exact on this host) or
-    a wrapper of logistic_pmfs_c."""
+    (CState); pmf = "torch" (the reference's expression on torch CPU), "cuda" (the same
+    expression on torch CUDA -- how the reference itself runs it) or "c" (libm, ans_oracle.c)."""
 
     def __init__(self, cfg, model, zendpoints, zcentres, coder="c", pmf="torch", trace=None):
-        from bitswap_b200.rand import ImageBins     # host-side table helper with the reference's formula
         self.cfg, self.model = cfg, model
         self.zend, self.zcen = zendpoints.double(), zcentres.double()
-        xb = ImageBins(torch.float64, "cpu", cfg.xdim)
-        self.xend, self.xcen = xb.endpoints(), xb.centres()
+        # ImageBins (utils/torch/rand.py:146-152): 255 inner endpoints, 256 centres, identical for every dimension
+        k = torch.arange(1, 256, dtype=torch.float64)
+        self.xend = (((k - 127.5) / 127.5) - 1. / 255.)[None,].expand([cfg.xdim, -1])
+        k = torch.arange(0, 256, dtype=torch.float64)
+        self.xcen = ((k - 127.5) / 127.5)[None,].expand([cfg.xdim, -1])
         self.coder_kind, self.pmf_kind, self.trace = coder, pmf, trace
         self.zr, self.xr = torch.arange(cfg.zdim), torch.arange(cfg.xdim)
         self.mu_hook = None     # optional: callable(kind, level, mu, scale) -> (mu, scale) to inject GPU nets
@@ -335,6 +337,11 @@ class BitSwapOracle:
     def _pmfs(self, endpoints, mu, scale):
         if self.pmf_kind == "torch":
             return logistic_pmfs_torch(endpoints, mu, scale).numpy()
+        if self.pmf_kind == "cuda":
+            # the reference's tensor expression evaluated where the reference evaluates it: on the GPU (device=f"cuda:{gpu}",
+            # cifar_compress.py:77,182-184).  torch-CUDA's float64 sigmoid is what the product's float64 cdf is bit-matched
+            # to, so with this kind EVERY stream must be bit-identical (no 1-ulp libm/Sleef bin flips).
+            return logistic_pmfs_torch(endpoints.cuda(), mu.cuda(), scale.cuda()).cpu().numpy()
         return logistic_pmfs_c(endpoints.numpy(), mu.numpy(), scale.numpy())
 
     def _coder(self, pmfs, q):

@@ -73,6 +73,43 @@ def test_underflow_and_overflow_map_to_reference_exceptions():
         ss.raise_on_error()
 
 
+def test_out_of_range_symbols_raise_index_error_like_the_reference():
+    """the reference indexes self.pmfs[i, s] (cifar_compress.py:50) -- a symbol outside the support or a symbol
+    vector of the wrong length is an IndexError there; here it must neither read device memory out of bounds nor
+    silently corrupt the stream."""
+    k = KATS[0]
+    pm, sym, st = _kat_inputs(k)
+    a = ANS(torch.from_numpy(pm).cuda(), 31, k["q"])
+    bad = sym.copy(); bad[3] = k["S"]
+    with pytest.raises(IndexError):
+        a.encode(list(st), torch.from_numpy(bad))
+    with pytest.raises(IndexError):
+        a.encode(list(st), torch.from_numpy(sym[:-1]))
+    bad[3] = -1
+    with pytest.raises(IndexError):
+        a.encode(list(st), torch.from_numpy(bad))
+    # device-side check of the batched entry points: the stream is flagged, nothing is read out of bounds
+    S, L, B = k["S"], k["L"], 3
+    P, C = O.tables_c(pm, 31, k["q"])
+    dP, dC = torch.from_numpy(P.astype(np.uint32).view(np.int32)).cuda(), torch.from_numpy(C.astype(np.uint32).view(np.int32)).cuda()
+    s32 = torch.from_numpy(np.tile(sym, (B, 1)).astype(np.int32)).cuda()
+    s32[1, 7] = S + 5
+    ss = StreamSet(B, 4096)
+    ss.import_lists([st] * B)
+    check(lib().bsw_ans_push(ss.handle, 0, B, dP.data_ptr(), dC.data_ptr(), 0, 0, s32.data_ptr(), L, S, 31, cuda_stream_ptr()))
+    _, _, f = ss.sizes()
+    assert f.tolist() == [0, 4, 0]
+    with pytest.raises(IndexError):
+        ss.raise_on_error()
+    for mode in (0, 1):                                       # two-phase push, generic and affine-row kernels
+        ends = np.linspace(-6.5, 6.5, 65)[None, 1:-1].repeat(L, 0)
+        mu = np.zeros((B, L), dtype=np.float32); sc = np.full((B, L), 0.5, dtype=np.float32)
+        s16 = np.tile((sym % 64).astype(np.int16), (B, 1)); s16[2, 5] = 64
+        with pytest.raises(IndexError):
+            _run_2p(ends, mu, sc, 64, 6, [st] * B, s16, mode)
+        check(lib().bsw_set_rows_mode(-1))
+
+
 def test_bad_arguments_are_rejected():
     ss = StreamSet(2, 64)
     rc = lib().bsw_ans_push(ss.handle, 1, 2, None, None, 0, 0, None, 4, 4, 31, None)
