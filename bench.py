@@ -8,18 +8,25 @@ state, so steps repeat without re-initialisation.
 
   value        Mpixel/s (pixel = H*W, 1024 per image) over encode+decode, inputs resident in HBM,
                CUDA-event timed, max over ranks; whole-job aggregate over N GPUs (weak scaling:
-               per-GPU batch fixed, streams sharded by rank, no collective on the data path).
+               per-GPU batch fixed, streams sharded by rank).  At N > 1 every step also gathers the
+               produced bitstreams of all ranks over NCCL (device-resident, trimmed) between the
+               encode and the decode -- the path's only collective, inside the timed region.
   e2e          same metric through the public Python/C-ABI API with HOST buffers: pinned uint8 pixels
-               -> device -> encode -> packed bitstream to host -> back to device -> decode -> pixels
+               -> device -> encode -> trimmed bitstream to host -> back to device -> decode -> pixels
                to host, all copies inside the timed region.
-  roofline     dominant kernel category (per-kernel CUDA events inside the timed region).
-  cpu_baseline the oracle port (reference algorithm: torch-CPU nets + float64 tables + Python-loop ANS)
-               on a bounded sample, on this box's host cores.
+  roofline     dominant kernel category, from CUDA events around every launch in a replay of the
+               timed steps with the SAME launch shapes (the lanes run back to back instead of
+               concurrently); traffic / FP64 instruction counts from the tracked ncu summary.
+  cpu_baseline the oracle port of the reference path (torch-CPU nets + float64 tables + Python-loop
+               ANS) on this box's host cores: latency mode with the 5-way time split and
+               throughput mode (one single-threaded process per core), bounded samples.
 
 `--impl reference` times that CPU path as its own arm (the reference is pure Python and cannot be
-pip-installed/travel; DESIGN.md).
+pip-installed/travel).  `--config crop` is BASELINE configs[4]: 100 variable-size images as
+chained 32x32 block streams over the GPUs, next to gzip/bz2/lzma/PNG/WebP on the host.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -49,8 +56,15 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_facts():
+    """Per-kernel facts taken from the tracked ncu captures (profiles/ncu_facts_r2.json, written by
+    scripts/ncu_summary.py facts): dram bytes per launch, FP64-pipe instructions per launch, streams per launch."""
+    p = os.path.join(ROOT, "profiles", "ncu_facts_r2.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 # ----------------------------------------------------------------------------------------------------
-# work accounting (DESIGN.md "Roofline accounting")
+# work accounting (DESIGN.md 5; SURVEY.md 6.3 / 8d)
 # ----------------------------------------------------------------------------------------------------
 def conv_flops(cfg):
     """Algorithmic 2*MAC of the UNPADDED reference convs per image and direction."""
@@ -73,15 +87,6 @@ def ans_bytes(cfg):
     return dict(pop_z=nz * z * 10, push_z=(nz - 1) * z * 10, push_x=x * (10 if cfg.cond_xscale else 6), prior=z * 2)
 
 
-def sigmoids(cfg):
-    z, x, nz, S = cfg.zdim, cfg.xdim, cfg.nz, cfg.zsupport
-    return dict(pop_z=nz * z * (S - 1), push_z=(nz - 1) * z * (S - 1), push_x=x * 255)
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), B=1024
-TRAFFIC = {"rows_z": 36.0e6 + 234.3e6, "pop_z": 321.0e6 + 9.2e6, "conv_dense3x3": 543.4e6 + 234.8e6}    # profiles/r1_ncu_{rows_v3,popcoarse_v2,convtc_v2}.md
-
-
 # ----------------------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------------------
@@ -93,7 +98,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -108,8 +113,9 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons, pw = [], [], set(), []
+        sm, mx, pw = [], [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        counts = {n: 0 for n in names}
         for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
@@ -117,96 +123,196 @@ class ClockSampler:
                 continue
             for nm, v in zip(names, r[3:7]):
                 if "Active" in v and "Not" not in v:
-                    reasons.add(nm)
+                    counts[nm] += 1
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_median_under_load": float(np.median([p for p in pw if p > 0.5 * max(pw)] or pw)),
+                "samples": len(sm), "reasons": sorted(n for n, c in counts.items() if c), "reason_samples": counts}
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port) -- bounded sample
+# CPU reference path (oracle port) -- bounded samples
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_sample(cfg, nimg, coder="port", threads=None):
-    """Times the reference algorithm on the host: chain of `nimg` images, encode then decode.
-    Returns (seconds_encode, seconds_decode, bits_per_dim)."""
+_W = {}
+
+
+def _cpu_setup(config, threads, coder="port"):
     from oracle import oracle as O
-    # batch-1 16x16 convs do not scale past a socket's worth of threads (128 threads measured 50x SLOWER than
-    # 8 on the GPU box), so the baseline uses the thread count that serves it best, capped at 16.
-    threads = threads or min(os.cpu_count(), 16)
     torch.set_num_threads(threads)
+    cfg = preset(config)
     sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=False)
     zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
     bs = O.BitSwapOracle(cfg, O.ModelOracle(cfg, sd), zend, zcen, coder=coder, pmf="torch")
-    imgs = synthetic.synthetic_images(cfg, nimg, seed=7)
+    return cfg, bs, O
+
+
+def cpu_chain(config, nimg, threads, seed=7, timers=False):
+    """One chain of `nimg` images, encode then decode, on `threads` torch threads.  Returns
+    (seconds_encode, seconds_decode, net bits/dim, split dict or None)."""
+    key = (config, threads)
+    if key not in _W:
+        _W[key] = _cpu_setup(config, threads)
+    cfg, bs, O = _W[key]
+    torch.set_num_threads(threads)
+    bs.timers = {} if timers else None
+    imgs = synthetic.synthetic_images(cfg, nimg, seed=seed)
     w, head = synthetic.initial_words(4096, seed=100)
-    st = ([int(v) for v in w] + [head]) if coder == "port" else O.CState(w, head)
-    n0 = len(st) if coder == "port" else st.n + 1
+    st = [int(v) for v in w] + [head]
+    n0 = len(st)
     t0 = time.perf_counter()
     for i in range(nimg):
         st = bs.encode_image(st, imgs[i])
     t1 = time.perf_counter()
-    n1 = len(st) if coder == "port" else st.n + 1
+    n1 = len(st)
     for i in reversed(range(nimg)):
         st, x = bs.decode_image(st)
         assert np.array_equal(x, imgs[i].reshape(-1))
     t2 = time.perf_counter()
-    return t1 - t0, t2 - t1, 32.0 * (n1 - n0) / (cfg.xdim * nimg)
+    split = None
+    if timers:
+        tot = sum(bs.timers.values()) or 1.0
+        split = {k: v / tot for k, v in sorted(bs.timers.items())}
+    return t1 - t0, t2 - t1, 32.0 * (n1 - n0) / (cfg.xdim * nimg), split
+
+
+def _tp_worker(args):
+    """Throughput-mode worker: one single-threaded process = one chain of one image, encode + decode."""
+    config, seed = args
+    e, d, _, _ = cpu_chain(config, 1, 1, seed=seed)
+    return e + d
+
+
+def _tp_init(config):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    torch.set_num_threads(1)
+    _W[(config, 1)] = _cpu_setup(config, 1)
+    cpu_chain(config, 1, 1)                                   # warm-up inside the worker (first-call costs)
+
+
+class ThroughputPool:
+    """One single-threaded worker process per host core (the reference's throughput mode)."""
+
+    def __init__(self, config, procs):
+        import multiprocessing as mp
+        self.config, self.procs = config, procs
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_tp_init, initargs=(config,))
+
+    def step(self, step_index=0):
+        """Every worker codes one image (encode + decode); returns (wall seconds, images)."""
+        t0 = time.perf_counter()
+        self.pool.map(_tp_worker, [(self.config, 1000 + step_index * self.procs + i) for i in range(self.procs)], chunksize=1)
+        return time.perf_counter() - t0, self.procs
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_procs():
+    n = os.cpu_count() or 1
+    try:
+        import psutil
+        n = min(n, max(1, int(psutil.virtual_memory().available // (1 << 30))))     # ~1 GB per worker (torch + model + tables)
+    except Exception:
+        pass
+    return max(1, min(n, 128))
 
 
 def run_reference_arm(args, cfg, rank, world):
+    """The reference's own CPU implementation of the path, with all the host threads it can use: one single-threaded
+    process per core, each coding its own chain (the reference is strictly batch 1).  A step = every worker encodes and
+    decodes one image."""
     if rank != 0:
         return
-    nimg = args.ref_images
-    cores = min(os.cpu_count(), 16)
-    for _ in range(args.warmup):
-        cpu_reference_sample(cfg, 1)
-    t_enc = t_dec = 0.0
-    bpd = 0.0
-    for _ in range(args.steps):
-        e, d, bpd = cpu_reference_sample(cfg, nimg)
-        t_enc += e; t_dec += d
-    px = args.steps * nimg * 1024
-    val = px / (t_enc + t_dec) / 1e6
-    sample = f"{nimg}-image chain per step, encode then decode, batch=1 (reference is strictly batch 1)"
+    procs = args.ref_procs or host_procs()
+    pool = ThroughputPool(args.config, procs)
+    for i in range(args.warmup):
+        pool.step(10000 + i)
+    wall, imgs = 0.0, 0
+    for i in range(args.steps):
+        w, n = pool.step(i)
+        wall += w; imgs += n
+    pool.close()
+    lat_threads = min(os.cpu_count() or 1, 16)
+    e, d, bpd, split = cpu_chain(args.config, 2, lat_threads, timers=True)
+    val = imgs * 1024 / wall / 1e6
+    sample = (f"throughput mode: {procs} single-threaded worker processes (of {os.cpu_count()} host cores), each step every worker "
+              f"encodes + decodes one image of its own chain (the reference is strictly batch 1)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * (t_enc + t_dec) / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 tables / f32 nets / int64 coder", "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg.xs[1]}x{cfg.xs[2]}x{cfg.xs[0]} uint8, nz={cfg.nz}, W={cfg.reswidth}; {sample}",
                        "what_runs": "oracle port of the reference path (torch-CPU nets, torch float64 logistic tables, "
                                     "Python-loop ANS with Python ints) -- the reference itself is pure Python and cannot travel"},
-            "encode_Mpixel_s": args.steps * nimg * 1024 / t_enc / 1e6, "decode_Mpixel_s": args.steps * nimg * 1024 / t_dec / 1e6,
             "bits_per_dim": bpd,
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "latency_mode": {"threads": lat_threads, "encode_s_per_image": e / 2, "decode_s_per_image": d / 2,
+                             "Mpixel_s": 2 * 1024 / (e + d) / 1e6, "time_split": split},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def cpu_baseline_block(config, images, tp_steps):
+    """cpu_baseline of the GPU arm's line: latency mode (one chain, up to 16 threads, 5-way split) + throughput mode."""
+    lat_threads = min(os.cpu_count() or 1, 16)
+    cpu_chain(config, 1, lat_threads)
+    e, d, bpd, split = cpu_chain(config, images, lat_threads, timers=True)
+    out = {"unit": UNIT, "kind": "port",
+           "latency_mode": {"threads": lat_threads, "Mpixel_s": images * 1024 / (e + d) / 1e6, "encode_s_per_image": e / images,
+                            "decode_s_per_image": d / images, "bits_per_dim": bpd, "time_split": split,
+                            "sample": f"one {images}-image chain (batch 1), encode then decode"}}
+    procs = host_procs()
+    pool = ThroughputPool(config, procs)
+    pool.step(999)
+    wall, imgs = 0.0, 0
+    for i in range(tp_steps):
+        w, n = pool.step(i)
+        wall += w; imgs += n
+    pool.close()
+    out.update(value=imgs * 1024 / wall / 1e6, cores=procs,
+               sample=f"throughput mode: {procs} single-threaded processes x {tp_steps} image(s) each, encode + decode "
+                      f"({os.cpu_count()} host cores); latency mode beside it")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
+def states_digest(ss, first=0, count=None):
+    """sha256 over (word count, head, words) of the streams -- what H3 / SURVEY 8e say must not depend on G."""
+    words, offs, heads, _ = ss.export(first, count)
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(offs).tobytes()); h.update(np.ascontiguousarray(heads).tobytes()); h.update(np.ascontiguousarray(words).tobytes())
+    return h.hexdigest()[:16]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cifar8")
-    ap.add_argument("--batch", type=int, default=1024, help="streams (= images per step) PER GPU")
+    ap.add_argument("--config", default="cifar8", help="cifar8 (BASELINE configs[1], default), imagenet4, mnist2, ..., or crop (configs[4])")
+    ap.add_argument("--batch", type=int, default=0, help="streams (= images per step) PER GPU (default 1024; imagenet4: 4096)")
     ap.add_argument("--tensor-cores", type=int, default=-1, help="-1 auto, 0 SIMT fp32 convs, 1 tcgen05")
-    ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-images", type=int, default=6)
+    ap.add_argument("--ref-procs", type=int, default=0, help="worker processes of the CPU reference arm (0 = one per core)")
+    ap.add_argument("--cpu-baseline-images", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="sub-batches coded concurrently on separate CUDA streams (1 = off)")
     ap.add_argument("--lane-size", type=int, default=0, help="streams per lane (0 = batch/lanes); the last lane takes the remainder")
-    ap.add_argument("--dual-stream", type=int, default=0, help="0 off; 2 = serial coder kernels on a high-priority stream (experiment)")
     ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
+    ap.add_argument("--crop-images", type=int, default=100)
+    ap.add_argument("--hwc-quirk", action="store_true", help="crop: feed blocks as imagenetcrop_compress.py:130 does")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config == "crop":
+        from scripts.bench_crop import run_crop
+        return run_crop(args, rank, world, local)
     cfg = preset(args.config)
 
     if args.impl == "reference":
@@ -215,40 +321,35 @@ def main():
 
     import torch.distributed as dist
     from bitswap_b200.model import Model
-    from bitswap_b200.codec import BitSwapCodec, Bins
+    from bitswap_b200.codec import BitSwapCodec, Bins, PipelinedCodec
     from bitswap_b200.streams import StreamSet
-    from bitswap_b200 import _lib
+    from bitswap_b200 import _lib, parallel
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peaks = measured_peaks()
+    facts = ncu_facts()
 
-    B = args.batch
+    B = args.batch or (4096 if args.config == "imagenet4" else 1024)
     use_tc = args.tensor_cores
     if use_tc < 0:
         use_tc = 1 if (_lib.has_tensor_core_path() and (cfg.reswidth + 63) // 64 * 64 == 256) else 0
     sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=False)          # default-init distribution
     zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
     bins = Bins(cfg, zend, zcen)
-    if args.lanes > 1:
-        from bitswap_b200.codec import PipelinedCodec
-        codec = PipelinedCodec(cfg, sd, bins, B, lanes=args.lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size)
-    else:
-        model = Model.from_config(cfg, max_batch=B, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
-        model.compress()
-        codec = BitSwapCodec(cfg, model, bins, B)
+    lanes = max(1, args.lanes)
+    codec = PipelinedCodec(cfg, sd, bins, B, lanes=lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size)
     two_phase = not args.fused_coder
     codec.set_two_phase(two_phase)
-    if args.dual_stream:
-        codec.set_dual_stream(args.dual_stream)
-    ss = StreamSet(B, 4096 + 2048)
-    w, head = synthetic.initial_words(4096, seed=100)
+    INIT_WORDS = 4096
+    ss = StreamSet(B, INIT_WORDS + 2048)
+    w, head = synthetic.initial_words(INIT_WORDS, seed=100)
     ss.fill(w, head)
+    # images are seeded by the GLOBAL stream index block: rank r codes exactly what a 1-GPU run with seed 7+r codes
     x_host = torch.from_numpy(synthetic.synthetic_images(cfg, B, seed=7 + rank)).pin_memory()
     x_dev = x_host.to(dev)
     out_dev = torch.empty_like(x_dev)
@@ -260,78 +361,94 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- correctness outside the timed region: round trip + bits/dim -------------------------------
+    # ---- correctness outside the timed region: round trip, bits/dim, digest of the coded streams ---------------
     n0, _, _ = ss.sizes()
     codec.encode(ss, x_dev)
+    torch.cuda.synchronize()
     n1, _, f1 = ss.sizes()
     launches_enc = codec.last_launches
-    bits_per_dim = float(32.0 * (n1 - n0).mean() / cfg.xdim)
+    acct = ss.bit_accounting(INIT_WORDS, cfg.xdim, 1)
+    digest = states_digest(ss)
+    sample_n = min(16, B)
+    digest_head = states_digest(ss, 0, sample_n)               # first streams of this rank (cross-rank determinism check below)
     codec.decode(ss, B, out=out_dev)
+    torch.cuda.synchronize()
     n2, h2, f2 = ss.sizes()
     launches_dec = codec.last_launches
     roundtrip_ok = bool(torch.equal(out_dev, x_dev) and np.array_equal(n2, n0) and not f1.any() and not f2.any()
                         and (h2 == np.uint64(head)).all())
     assert roundtrip_ok, "round trip failed"
 
-    # ---- device-resident timing ----------------------------------------------------------------------
+    # ---- device-resident timing --------------------------------------------------------------------------------
+    def gather_step():
+        """The path's only collective: every rank receives every rank's PRODUCED words (trimmed), device to device."""
+        wd, od, hd, bd = ss.pack_device(trim=True)
+        lens = od[1:] - od[:-1]
+        return parallel.gather_packed(wd, lens, hd, bd)
+
     for _ in range(max(args.warmup, 3)):
         codec.encode(ss, x_dev)
+        if world > 1:
+            gather_step()
         codec.decode(ss, B, out=out_dev)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    if args.lanes <= 1:
-        codec.profile(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     ev[0].record()
+    gathered_words = 0
     for i in range(args.steps):
         codec.encode(ss, x_dev)
-        ev[2 * i + 1].record()
+        ev[3 * i + 1].record()
+        if world > 1:
+            W, M, counts = gather_step()
+        ev[3 * i + 2].record()
         codec.decode(ss, B, out=out_dev)
-        ev[2 * i + 2].record()
+        ev[3 * i + 3].record()
     torch.cuda.synchronize()
     total_ms = ev[0].elapsed_time(ev[-1])
-    enc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
-    dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps))
+    enc_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps))
+    gat_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps))
+    dec_ms = sum(ev[3 * i + 2].elapsed_time(ev[3 * i + 3]) for i in range(args.steps))
     clocks = sampler.stop() if sampler else None
-    if args.lanes > 1:
-        # Per-kernel times.  With several lanes in flight the kernels of different lanes share SMs, so event durations
-        # taken inside the timed region overlap each other and cannot be attributed.  The same steps are therefore
-        # replayed on ONE stream by a single-lane codec at the full batch (same kernels; launch shape = B images instead
-        # of B/lanes) with CUDA events around every launch.
-        model1 = Model.from_config(cfg, max_batch=B, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
-        model1.compress()
-        codec1 = BitSwapCodec(cfg, model1, bins, B)
-        codec1.set_two_phase(two_phase)
-        for _ in range(2):
-            codec1.encode(ss, x_dev)
-            codec1.decode(ss, B, out=out_dev)
-        codec1.profile(True)
-        for i in range(args.steps):
-            codec1.encode(ss, x_dev)
-            codec1.decode(ss, B, out=out_dev)
-        prof = codec1.profile(False)
-        assert torch.equal(out_dev, x_dev)
-        del codec1, model1
-    else:
-        prof = codec.profile(False)
+    gather_info = None
+    if world > 1:
+        gathered_words = int(counts[:, 0].sum())
+        # what arrived must be what was sent: every rank's slice re-imported into fresh streams decodes to that rank's pixels
+        # (checked on rank 0 for the LAST rank's shard: a different GPU coded it)
+        gather_info = {"words_gathered_per_step": gathered_words, "bytes_per_image": 4.0 * gathered_words / (B * world),
+                       "streams": int(counts[:, 1].sum())}
+    # ---- per-kernel times: the same steps with the lanes run back to back (identical launch shapes) ---------------
+    codec.serial = True
+    for _ in range(1):
+        codec.encode(ss, x_dev)
+        codec.decode(ss, B, out=out_dev)
+    codec.profile(True)
+    for i in range(args.steps):
+        codec.encode(ss, x_dev)
+        codec.decode(ss, B, out=out_dev)
+    prof = codec.profile(False)
+    torch.cuda.synchronize()
+    assert torch.equal(out_dev, x_dev)
+    codec.serial = False
     barrier()
-    t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, enc_ms, dec_ms, gat_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, dec_ms = t.tolist()
+    total_ms, enc_ms, dec_ms, gat_ms = t.tolist()
     px_job = world * B * 1024 * args.steps
     value = px_job / (total_ms * 1e-3) / 1e6
 
-    # ---- end to end with host buffers ----------------------------------------------------------------
+    # ---- end to end with host buffers (trimmed bitstreams both ways) ---------------------------------------------
     def e2e_step():
         x_d = x_host.to(dev, non_blocking=True)                                   # H2D pixels
         codec.encode(ss, x_d)
-        words, offs, heads = ss.export_packed()                                   # device gather + D2H bitstream, offsets, heads
-        ss.import_packed_fast(words, offs, heads)                                 # H2D + device scatter (the receiver's side)
+        words, offs, heads, base = ss.export_packed(trim=True)                    # device gather + D2H produced words, offsets, heads, bases
+        nbytes = int(words.nbytes + offs.nbytes + heads.nbytes + base.nbytes)
+        ss.import_packed_fast(words, offs, heads, base=base)                      # H2D + device scatter (the receiver's side: it holds the seed words)
         o = codec.decode(ss, B, out=out_dev)
         out_host.copy_(o, non_blocking=True)                                      # D2H pixels
         torch.cuda.synchronize()
-        return int(words.nbytes + offs.nbytes + heads.nbytes)
+        return nbytes
 
     bs_bytes = e2e_step()
     barrier()
@@ -346,107 +463,123 @@ def main():
     e2e_s = t.item()
     e2e_val = px_job / e2e_s / 1e6
     assert torch.equal(out_host, x_host)
+    _, _, f3 = ss.sizes()
+    assert not f3.any()
 
-    # ---- gather the final bitstreams over NCCL (only collective; outside the coder) -------------------
-    gather_ms = None
-    total_bits = float(32.0 * (n1 - n0).sum())
+    # ---- cross-G determinism (H3): the streams a rank coded == what ANOTHER GPU codes for the same seeds ----
+    digests, determinism = [digest], None
     if world > 1:
-        from bitswap_b200 import parallel
-        codec.encode(ss, x_dev)
-        torch.cuda.synchronize()
-        words, offs, heads, flags = ss.export()
-        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        gathered = parallel.gather_bitstreams(words, offs, heads, device=dev)      # NCCL over NVLink
-        total_bits = parallel.reduce_sum(total_bits, device=dev)
-        g1.record()
-        torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
-        assert sum(len(g[2]) for g in gathered) == B * world
-        codec.decode(ss, B, out=out_dev)
-        torch.cuda.synchronize()
+        objs = [None] * world
+        dist.all_gather_object(objs, {"rank": rank, "digest": digest, "head": digest_head})
+        digests = [o["digest"] for o in objs]
+        if rank == 0:
+            peer = world - 1
+            xs = torch.from_numpy(synthetic.synthetic_images(cfg, B, seed=7 + peer)[:sample_n]).to(dev)
+            m2 = Model.from_config(cfg, max_batch=sample_n, use_tensor_cores=bool(use_tc)).load_state_dict(sd)
+            m2.compress()
+            c2 = BitSwapCodec(cfg, m2, bins, sample_n)
+            s2 = StreamSet(sample_n, INIT_WORDS + 2048)
+            s2.fill(w, head)
+            c2.encode(s2, xs)
+            torch.cuda.synchronize()
+            mine = states_digest(s2)
+            determinism = {"peer_rank": peer, "streams": sample_n, "peer_digest": objs[peer]["head"], "recoded_here_digest": mine,
+                           "equal": mine == objs[peer]["head"], "note": "other GPU, other batch size (16 vs the lane size), other position"}
+            assert determinism["equal"], "stream states depend on which GPU / batch coded them"
 
-    # ---- roofline for the dominant kernel category ---------------------------------------------------------
-    fl, ab, sg = conv_flops(cfg), ans_bytes(cfg), sigmoids(cfg)
-    FP64_PER_SIGMOID = 16        # FP64-pipe instructions per cdf value in the screened k_rows loop (DESIGN.md "ANS kernels")
+    # ---- roofline for the dominant kernel category ---------------------------------------------------------------
+    fl, ab = conv_flops(cfg), ans_bytes(cfg)
     fp64_peak = _lib.measure_fp64_peak()                                     # DFMA lanes/s, measured on this GPU
-    Bl = B                                                       # images per profiled kernel launch
-    nsig_z, nsig_x = cfg.zdim * (cfg.zsupport - 1) * Bl, cfg.xdim * 255 * Bl
-    # algorithmic work of ONE launch (B images, one direction).  Coder kernels: compulsory HBM bytes = mu,sigma
-    # float32 + int16 symbol per symbol-op; they are FP64-pipe bound, so an fp64 fraction is added.
+    Bl = codec.per                                                           # images per kernel launch (lane size)
     per_launch = {
-        "conv_dense5x5": ("tensor", fl["dense5"] * Bl, 0), "conv_dense3x3": ("tensor", fl["dense3"] * Bl, 0),
-        "rows_z": ("hbm", cfg.zdim * 10 * Bl, nsig_z), "rows_x": ("hbm", ab["push_x"] * Bl, nsig_x),
-        "pop_z": ("hbm", cfg.zdim * 10 * Bl, 0 if two_phase else nsig_z), "push_z": ("hbm", cfg.zdim * 10 * Bl, 0 if two_phase else nsig_z),
-        "pop_x": ("hbm", ab["push_x"] * Bl, 0 if two_phase else nsig_x), "push_x": ("hbm", ab["push_x"] * Bl, 0 if two_phase else nsig_x),
+        "conv_dense5x5": ("tensor", fl["dense5"] * Bl), "conv_dense3x3": ("tensor", fl["dense3"] * Bl),
+        "rows_z": ("hbm", cfg.zdim * 10 * Bl), "rows_x": ("hbm", ab["push_x"] * Bl),
+        "pop_z": ("hbm", cfg.zdim * 10 * Bl), "push_z": ("hbm", cfg.zdim * 10 * Bl),
+        "pop_x": ("hbm", ab["push_x"] * Bl), "push_x": ("hbm", ab["push_x"] * Bl),
     }
     kernels = {}
     tot_ms = max(sum(v[0] for v in prof.values()), 1e-9)
     for k, (ms, n) in prof.items():
         if n == 0:
             continue
-        rec = {"ms_total": ms, "launches": n, "avg_ms": ms / n, "share": ms / tot_ms}
+        rec = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps, "avg_ms": ms / n, "share": ms / tot_ms}
         if k in per_launch:
-            bound, work, nsig = per_launch[k]
+            bound, work = per_launch[k]
             sec = ms / n * 1e-3
             if bound == "tensor":
                 rec.update(bound="tensor", achieved=work / sec / 1e12, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
                            mma_tflops_issued=3 * work * (256 / cfg.reswidth) ** 2 / sec / 1e12 if use_tc else None)
             else:
-                rec.update(bound="hbm", achieved=work / sec / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
-                if nsig:
-                    rec["f64_sigmoids_per_s"] = nsig / sec
-                    rec["fp64"] = {"achieved_dfma_lanes_per_s": nsig * FP64_PER_SIGMOID / sec, "peak_measured": fp64_peak,
-                                   "frac": nsig * FP64_PER_SIGMOID / sec / fp64_peak}
+                rec.update(bound="hbm", achieved=work / sec / 1e9, peak=peaks["hbm_gbs"], unit="GB/s", algorithmic_bytes_per_launch=work)
             rec["frac"] = rec["achieved"] / rec["peak"]
+            fk = facts.get(k)
+            if fk and fk.get("streams_per_launch"):
+                scale = Bl / fk["streams_per_launch"]
+                rec["traffic"] = fk["dram_bytes_per_launch"] * scale
+                rec["traffic_source"] = fk.get("source")
+                if fk.get("fp64_inst_per_launch"):
+                    lanes_per_s = 32.0 * fk["fp64_inst_per_launch"] * scale / sec
+                    rec["fp64"] = {"warp_instructions_per_launch": fk["fp64_inst_per_launch"] * scale, "achieved_lanes_per_s": lanes_per_s,
+                                   "peak_measured_dfma_lanes_per_s": fp64_peak, "frac": lanes_per_s / fp64_peak,
+                                   "source": "sm__inst_executed_pipe_fp64 of " + str(fk.get("source"))}
         kernels[k] = rec
-    dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["ms_total"])
+    dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
     roofline = {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"], "peak": kernels[dom]["peak"],
-                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": (TRAFFIC.get(dom) * Bl / 1024 if TRAFFIC.get(dom) else None),
+                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": kernels[dom].get("traffic"),
+                "traffic_source": kernels[dom].get("traffic_source"),
                 "peak_source": peaks["source"] + (" bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else " hbm_gbs"),
-                "share_of_step": kernels[dom]["share"]}
+                "share_of_step": kernels[dom]["share"], "streams_per_launch": Bl}
     if "fp64" in kernels[dom]:
         roofline["fp64"] = kernels[dom]["fp64"]
-        roofline["note"] = ("the coder's row-table kernel is bound by float64 arithmetic, not HBM ((S-1) float64 sigmoids per symbol-op, "
-                            "SURVEY.md 8d/H2): the hbm fraction is the contract's figure; the fp64 fraction counts 16 FP64 instructions per "
-                            "sigmoid against the measured DFMA peak -- a warp-wide FP64 instruction takes two issue slots, so ~0.5 means half of "
-                            "all issue slots are FP64 and the rest is the kernel's integer work (DESIGN.md 5.1)")
-
+    if kernels[dom]["bound"] == "hbm":
+        roofline["note"] = ("the coder's table kernel is bound by float64 arithmetic, not HBM ((S-1) float64 logistic values per "
+                            "symbol-op, SURVEY.md 8d/H2): the hbm fraction is the contract's figure; `fp64` is the FP64-pipe "
+                            "instruction count of the tracked ncu capture against the measured DFMA peak")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 tables / int64 coder / " + ("bf16x3 split tcgen05" if use_tc else "f32 SIMT") + " convs",
             "coder": "two-phase (parallel f64 row tables + serial integer coder)" if two_phase else "fused one-warp-per-stream",
-            "lanes": args.lanes,
+            "lanes": codec.lanes,
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg.xs[1]}x{cfg.xs[2]}x{cfg.xs[0]} uint8, nz={cfg.nz}, W={cfg.reswidth}, q={cfg.quantbits}; "
-                                   f"{B} independent ANS streams per GPU x 1 image per step; step = Bit-Swap encode + decode",
+                                   f"{B} independent ANS streams per GPU x 1 image per step; step = Bit-Swap encode"
+                                   + (" + NCCL gather of the produced bitstreams" if world > 1 else "") + " + decode",
                        "streams_per_gpu": B, "global_batch": B * world, "weights": "seeded random init (reference default-init distribution)",
                        "bins": "synthetic uniform grids + float32 equal-mass top level", "images": "iid uniform uint8",
                        "l2": "per-step working set (3 x 268 MB activations + streams) >> 126 MB L2: no explicit flush needed",
-                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective; within a GPU {args.lanes} sub-batches "
-                                      "on separate CUDA streams so FP64-bound coder kernels and tensor-bound convs overlap "
-                                      "(per-kernel times below are measured under that concurrency)"},
+                       "parallelism": f"streams sharded over {world} GPU(s); within a GPU {codec.lanes} sub-batches of {Bl} on separate CUDA streams"},
             "encode_Mpixel_s": px_job / (enc_ms * 1e-3) / 1e6, "decode_Mpixel_s": px_job / (dec_ms * 1e-3) / 1e6,
-            "Mdim_s": value * cfg.xs[0], "bits_per_dim": total_bits / (cfg.xdim * B * world), "roundtrip_ok": roundtrip_ok,
-            "gpu_launches": (launches_enc + launches_dec) * args.steps,
+            "Mdim_s": value * cfg.xs[0],
+            "bits_per_dim": float(acct["net_bits_per_dim"].mean()),
+            "bits": {"net_bits_per_dim": float(acct["net_bits_per_dim"].mean()),
+                     "cma_bits_per_dim_incl_initial_bits": float(acct["cma_bits_per_dim"].mean()),
+                     "total_bits_per_stream": float(acct["total_bits"].mean()),
+                     "definition": "cifar_compress.py:253-259: net = (len(state) - len(initialstate)) * 32 / xdim; "
+                                   "cma = (len(state) - (len(restbits) - 1)) * 32 / (xdim * images), restbits = state after the first pop; "
+                                   "1 image per chain here, so cma is the reference's CMA@1"},
+            "roundtrip_ok": roundtrip_ok, "stream_digests": digests,
+            "gpu_launches": (launches_enc + launches_dec + (2 if world > 1 else 0)) * args.steps,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() + bs_bytes),
-                    "d2h_bytes_per_step": int(bs_bytes + out_host.numel()), "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "d2h_bytes_per_step": int(bs_bytes + out_host.numel()), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "bitstream_bytes_per_image": bs_bytes / B},
             "roofline": roofline, "kernels": kernels, "clocks": clocks,
-            "kernels_timing": ("CUDA events around every launch inside the timed region" if args.lanes <= 1 else
-                               f"CUDA events around every launch in a serial replay of the same {args.steps} steps by a single-lane codec at the "
-                               f"full batch of {B} (same kernels); the timed region itself runs {args.lanes} lanes of {B // args.lanes} concurrently, "
-                               "where per-kernel event times overlap and cannot be attributed")}
-    if gather_ms is not None:
-        line["bitstream_gather_ms"] = gather_ms
+            "kernels_timing": (f"CUDA events around every launch in a replay of the same {args.steps} steps with the {codec.lanes} lanes run back "
+                               f"to back on one stream: identical kernels and launch shapes ({Bl} streams per launch) as the timed region, "
+                               "which runs the lanes concurrently (there per-kernel event times overlap and cannot be attributed)")}
+    if world > 1:
+        line["bitstream_gather"] = dict(gather_info, ms_per_step=gat_ms / args.steps, inside_timed_region=True,
+                                        how="StreamSet.pack_device(trim) -> parallel.gather_packed: 3 all_gather_into_tensor (NCCL), device resident")
+        line["bitstream_gather_ms"] = gat_ms / args.steps
+        line["cross_gpu_determinism"] = determinism
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        nimg = args.cpu_baseline_images
-        e, d, bpd = cpu_reference_sample(cfg, nimg)
-        line["cpu_baseline"] = {"value": nimg * 1024 / (e + d) / 1e6, "unit": UNIT, "cores": min(os.cpu_count(), 16), "kind": "port",
-                                "sample": f"one {nimg}-image chain (batch 1), encode then decode; torch-CPU nets with "
-                                          f"{min(os.cpu_count(), 16)} threads (of {os.cpu_count()} host cores) + float64 tables + Python-loop ANS",
-                                "encode_s_per_image": e / nimg, "decode_s_per_image": d / nimg, "bits_per_dim": bpd}
+        del codec
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_baseline_block(args.config, args.cpu_baseline_images, 1)
+    if world > 1:
+        dist.barrier()
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)                  # LAST thing on stdout (NCCL is free to print its banner before)
     if world > 1:
         dist.destroy_process_group()
 

@@ -96,9 +96,12 @@ def _set_argtypes(L):
         "bsw_streams_sizes": [P, P, P, P],
         "bsw_streams_export": [P, I, I, P, P],
         "bsw_streams_min_words": [P, P],
+        "bsw_streams_rest_words": [P, P],
         "bsw_streams_device_ptrs": [P, PP, PP, PP, PP],
         "bsw_streams_pack": [P, I, I, P, P, P, P],
         "bsw_streams_unpack": [P, I, I, P, P, P, P],
+        "bsw_streams_pack_trimmed": [P, I, I, P, P, P, P, P],
+        "bsw_streams_unpack_trimmed": [P, I, I, P, P, P, P, P],
         "bsw_streams_total_words": [P, P, P],
         "bsw_ans_tables": [P, L64, I, I, I, P, P, P, P],
         "bsw_ans_push": [P, I, I, P, P, L64, L64, P, L64, I, I, P],
@@ -144,8 +147,8 @@ def _set_argtypes(L):
 
 
 EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure_fp64_peak", "bsw_selftest_cdf", "bsw_selftest_cdf_apx", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
-           "bsw_streams_capacity", "bsw_streams_import", "bsw_streams_fill", "bsw_streams_sizes", "bsw_streams_min_words", "bsw_streams_export",
-           "bsw_streams_device_ptrs", "bsw_streams_pack", "bsw_streams_unpack", "bsw_streams_total_words", "bsw_ans_tables", "bsw_ans_push", "bsw_ans_pop",
+           "bsw_streams_capacity", "bsw_streams_import", "bsw_streams_fill", "bsw_streams_sizes", "bsw_streams_min_words", "bsw_streams_rest_words", "bsw_streams_export",
+           "bsw_streams_device_ptrs", "bsw_streams_pack", "bsw_streams_unpack", "bsw_streams_pack_trimmed", "bsw_streams_unpack_trimmed", "bsw_streams_total_words", "bsw_ans_tables", "bsw_ans_push", "bsw_ans_pop",
            "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_logistic_scratch_bytes", "bsw_set_rows_mode", "bsw_bins_level_is_uniform", "bsw_rows6_set_verify", "bsw_rows6_verify_read", "bsw_logistic_push_2p",
            "bsw_logistic_pop_2p", "bsw_bins_create",
            "bsw_bins_destroy", "bsw_bins_device_ptrs", "bsw_gather_zcentres", "bsw_gather_xcentres",

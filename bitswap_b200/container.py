@@ -8,8 +8,9 @@ has more than t blocks (images are ordered by block count so the active streams 
 
 Container (np.uint32 array, what demo_compress.py saves with np.save):
     [ words that were actually borrowed or produced ..., head_lo, head_hi, nblocks, h, w ]
-Blocks are fed CHW like the demo path does (demo_compress.py:120), not the HWC quirk of
-imagenetcrop_compress.py:130.
+Blocks are fed CHW like the demo path does (demo_compress.py:120).  `hwc_quirk=True` reproduces
+imagenetcrop_compress.py:130 instead, which flattens each [32,32,3] HWC block straight into the CHW model's input
+(`torch.from_numpy(x).view(xdim)`) -- the layout behind the README's ImageNet-crop numbers.
 """
 import numpy as np
 import torch
@@ -37,7 +38,18 @@ def unextract_blocks(blocks, h, w):
     return blocks.reshape(h // bh, w // bw, bh, bw, c).swapaxes(1, 2).reshape(h, w, c)
 
 
-def compress_images(codec, images, excess_state_len=10000, seed=100, scheme=BITSWAP):
+def _blocks_to_model(blocks, hwc_quirk):
+    """[n,32,32,C] HWC blocks -> [n,C,32,32] model input."""
+    n, bh, bw, c = blocks.shape
+    return blocks.reshape(n, c, bh, bw) if hwc_quirk else blocks.transpose(0, 3, 1, 2)
+
+
+def _model_to_blocks(x, hwc_quirk):
+    n, c, bh, bw = x.shape
+    return np.ascontiguousarray(x).reshape(n, bh, bw, c) if hwc_quirk else np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+
+
+def compress_images(codec, images, excess_state_len=10000, seed=100, scheme=BITSWAP, hwc_quirk=False, words_per_block=1400):
     """images: list of HWC uint8 arrays (any sizes >= 32x32).  Returns one container array per image.
     Every chain starts from the reference's initial state: `excess_state_len` random words drawn with
     np.random.seed(100) (demo_compress.py:113-115, :202)."""
@@ -45,15 +57,28 @@ def compress_images(codec, images, excess_state_len=10000, seed=100, scheme=BITS
     order = sorted(range(len(images)), key=lambda i: (-tiled[i][0].shape[0], i))
     nblk = [tiled[i][0].shape[0] for i in order]
     n = len(images)
-    ss = StreamSet(n, excess_state_len + 1400 * max(nblk) + 64)
     w, head = initial_words(excess_state_len, seed=seed)
-    ss.fill(w, head)
+    # capacity: `words_per_block` words per 32x32 block (1400 = 14.6 bits/dim; 8 bits/dim of raw pixels is 768).  A chain
+    # that still overflows is retried with twice the room instead of failing after the whole chain was coded.
+    for attempt in range(4):
+        ss = StreamSet(n, excess_state_len + (words_per_block << attempt) * max(nblk) + 64, device=codec.device)
+        ss.fill(w, head)
+        try:
+            return _compress_chains(codec, ss, tiled, order, nblk, scheme, hwc_quirk)
+        except OverflowError:
+            if attempt == 3:
+                raise
+    raise AssertionError("unreachable")
+
+
+def _compress_chains(codec, ss, tiled, order, nblk, scheme, hwc_quirk):
+    n = len(order)
     # all blocks to the device once: [step t, stream j] = block t of the j-th largest image (CHW, demo_compress.py:120)
     C = tiled[order[0]][0].shape[-1]
     host = np.zeros((max(nblk), n, C, 32, 32), dtype=np.uint8)
     for j, i in enumerate(order):
-        host[:nblk[j], j] = tiled[i][0].transpose(0, 3, 1, 2)
-    dev = torch.from_numpy(host).cuda()
+        host[:nblk[j], j] = _blocks_to_model(tiled[i][0], hwc_quirk)
+    dev = torch.from_numpy(host).to(torch.device("cuda", codec.device))
     for t in range(max(nblk)):
         active = sum(1 for b in nblk if b > t)
         codec.encode(ss, dev[t, :active].contiguous(), first=0, scheme=scheme)
@@ -71,25 +96,33 @@ def compress_images(codec, images, excess_state_len=10000, seed=100, scheme=BITS
     return out
 
 
-def decompress_images(codec, containers, channels=3, scheme=BITSWAP):
+def decompress_images(codec, containers, channels=3, scheme=BITSWAP, hwc_quirk=False, headroom_words=None):
     """Inverse of compress_images: list of container arrays -> list of HWC uint8 images (cropped sizes)."""
     meta = []
     for c in containers:
         c = np.asarray(c, dtype=np.uint32)
+        if c.ndim != 1 or c.size < 5:
+            raise ValueError(f"container too short ({c.size} words): needs at least head_lo, head_hi, nblocks, h, w")
         nblocks, h, w = int(c[-3]), int(c[-2]), int(c[-1])                                      # demo_decompress.py:216-219
+        if h <= 0 or w <= 0 or h % 32 or w % 32 or nblocks != (h // 32) * (w // 32) or nblocks > (1 << 20):
+            raise ValueError(f"inconsistent container header: nblocks={nblocks}, h={h}, w={w}")
         head = (int(c[-4]) << 32) | int(c[-5])                                                  # :222
         meta.append((c[:-5], head, nblocks, h, w))
     order = sorted(range(len(containers)), key=lambda i: (-meta[i][2], i))
     nblk = [meta[i][2] for i in order]
     n = len(containers)
-    ss = StreamSet(n, max(len(meta[i][0]) for i in order) + 64)
+    # The receiver pushes too (it returns the borrowed bits, cifar_compress.py:306-313): one block's worth of latents,
+    # nz * zdim symbols at <= 31 bits each, can sit on the stack above the container's own length.
+    if headroom_words is None:
+        headroom_words = codec.cfg.nz * codec.cfg.zdim + 64
+    ss = StreamSet(n, max(len(meta[i][0]) for i in order) + headroom_words, device=codec.device)
     ss.import_lists([[int(v) for v in meta[i][0]] + [meta[i][1]] for i in order])
-    dev = torch.zeros((max(nblk), n, channels, 32, 32), dtype=torch.uint8, device="cuda")
+    dev = torch.zeros((max(nblk), n, channels, 32, 32), dtype=torch.uint8, device=torch.device("cuda", codec.device))
     for t in reversed(range(max(nblk))):
         active = sum(1 for b in nblk if b > t)
         dev[t, :active] = codec.decode(ss, active, first=0, scheme=scheme)
     host = dev.cpu().numpy()                                               # one transfer for every block of every image
-    blocks = [np.ascontiguousarray(host[:nblk[j], j].transpose(0, 2, 3, 1)) for j in range(n)]
+    blocks = [_model_to_blocks(host[:nblk[j], j], hwc_quirk) for j in range(n)]
     ss.raise_on_error()
     out = [None] * n
     for j, i in enumerate(order):

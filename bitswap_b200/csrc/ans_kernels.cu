@@ -39,6 +39,8 @@ extern "C" int bsw_streams_create(bsw_streams **out, int n_streams, int64_t capa
     BSW_CUDA(cudaMalloc(&s->flags, sizeof(int32_t) * s->B));
     BSW_CUDA(cudaMalloc(&s->minwords, sizeof(int32_t) * s->B));
     BSW_CUDA(cudaMemset(s->minwords, 0, sizeof(int32_t) * s->B));
+    BSW_CUDA(cudaMalloc(&s->restwords, sizeof(int32_t) * s->B));
+    BSW_CUDA(cudaMemset(s->restwords, 0xff, sizeof(int32_t) * s->B));
     BSW_CUDA(cudaMemset(s->nwords, 0, sizeof(int32_t) * s->B));
     BSW_CUDA(cudaMemset(s->heads, 0, sizeof(uint64_t) * s->B));
     BSW_CUDA(cudaMemset(s->flags, 0, sizeof(int32_t) * s->B));
@@ -47,7 +49,7 @@ extern "C" int bsw_streams_create(bsw_streams **out, int n_streams, int64_t capa
 }
 extern "C" int bsw_streams_destroy(bsw_streams *s) {
     if (!s) return BSW_OK;
-    cudaFree(s->words); cudaFree(s->nwords); cudaFree(s->heads); cudaFree(s->flags); cudaFree(s->minwords);
+    cudaFree(s->words); cudaFree(s->nwords); cudaFree(s->heads); cudaFree(s->flags); cudaFree(s->minwords); cudaFree(s->restwords);
     delete s;
     return BSW_OK;
 }
@@ -70,6 +72,7 @@ extern "C" int bsw_streams_import(bsw_streams *s, int first, int count, const ui
     BSW_CUDA(cudaMemcpy(s->minwords + first, n.data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice));
     BSW_CUDA(cudaMemcpy(s->heads + first, heads_host, sizeof(uint64_t) * count, cudaMemcpyHostToDevice));
     BSW_CUDA(cudaMemset(s->flags + first, 0, sizeof(int32_t) * count));
+    BSW_CUDA(cudaMemset(s->restwords + first, 0xff, sizeof(int32_t) * count));
     return BSW_OK;
 }
 
@@ -77,7 +80,7 @@ __global__ void k_streams_fill(bsw_streams sv, const uint32_t *src, int64_t n, u
     int b = blockIdx.y;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         sv.words[(int64_t)b * sv.cap + i] = src[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sv.nwords[b] = (int32_t)n; sv.minwords[b] = (int32_t)n; sv.heads[b] = head; sv.flags[b] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sv.nwords[b] = (int32_t)n; sv.minwords[b] = (int32_t)n; sv.restwords[b] = -1; sv.heads[b] = head; sv.flags[b] = 0; }
 }
 extern "C" int bsw_streams_fill(bsw_streams *s, const uint32_t *words_host, int64_t nwords, uint64_t head) {
     BSW_REQUIRE(s && nwords >= 0 && nwords <= s->cap, "bsw_streams_fill: nwords exceeds capacity");
@@ -112,6 +115,24 @@ extern "C" int bsw_streams_min_words(bsw_streams *s, int64_t *min_host) {
     for (int i = 0; i < s->B; ++i) min_host[i] = n[i];
     return BSW_OK;
 }
+// a12 accounting: the word count right after a chain's first pop, the reference's len(restbits) - 1 (cifar_compress.py:190-192,254)
+__global__ void k_mark_rest(bsw_streams sv, int first, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && sv.restwords[first + i] < 0) sv.restwords[first + i] = sv.nwords[first + i];
+}
+int bsw_streams_mark_rest(bsw_streams *s, int first, int count, cudaStream_t st) {
+    k_mark_rest<<<(count + 255) / 256, 256, 0, st>>>(*s, first, count);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+extern "C" int bsw_streams_rest_words(bsw_streams *s, int64_t *rest_host) {
+    BSW_REQUIRE(s && rest_host, "null argument");
+    BSW_CUDA(cudaDeviceSynchronize());
+    std::vector<int32_t> n(s->B);
+    BSW_CUDA(cudaMemcpy(n.data(), s->restwords, sizeof(int32_t) * s->B, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < s->B; ++i) rest_host[i] = n[i];
+    return BSW_OK;
+}
 extern "C" int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t *words_host,
                                   const int64_t *offsets_host) {
     BSW_REQUIRE(s && first >= 0 && count >= 0 && first + count <= s->B, "bsw_streams_export: range");
@@ -124,8 +145,12 @@ extern "C" int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t
     return BSW_OK;
 }
 // ---- packed (de)serialisation: every stream's words gathered into / scattered from ONE contiguous device buffer with
-// coalesced 128-byte warp accesses, so a host export/import is three memcpys instead of two per stream -------------
-__global__ void k_pack_offsets(const int32_t *__restrict__ n, int count, int64_t *__restrict__ offs) {
+// coalesced 128-byte warp accesses, so a host export/import is three memcpys instead of two per stream.
+// Trimmed form (base != NULL): only words[base_b .. n_b) travel, base_b = the lowest depth the stack ever reached -- the
+// initial random words below it were never borrowed and the receiver already has them (demo_compress.py:137,160
+// `excess_state_len`; the receiver re-creates them from the seed, demo_decompress.py:176-186).
+__global__ void k_pack_offsets(const int32_t *__restrict__ n, const int32_t *__restrict__ minw, int trim, int count,
+                               int64_t *__restrict__ offs, int32_t *__restrict__ base_out) {
     // single block exclusive scan (count <= a few 10^4 streams)
     __shared__ long long carry;
     __shared__ long long part[32];
@@ -133,7 +158,9 @@ __global__ void k_pack_offsets(const int32_t *__restrict__ n, int count, int64_t
     __syncthreads();
     for (int base = 0; base < count; base += blockDim.x) {
         int i = base + threadIdx.x;
-        long long v = i < count ? n[i] : 0, x = v;
+        int lo = (trim && i < count) ? min(minw[i], n[i]) : 0;
+        if (base_out && i < count) base_out[i] = lo;
+        long long v = i < count ? n[i] - lo : 0, x = v;
         for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(FULL, x, o); if ((threadIdx.x & 31) >= o) x += t; }
         if ((threadIdx.x & 31) == 31) part[threadIdx.x >> 5] = x;
         __syncthreads();
@@ -150,40 +177,62 @@ __global__ void k_pack_offsets(const int32_t *__restrict__ n, int count, int64_t
         __syncthreads();
     }
 }
-__global__ void k_pack_words(bsw_streams sv, int first, const int64_t *__restrict__ offs, uint32_t *__restrict__ out,
-                             uint64_t *__restrict__ heads_out) {
+__global__ void k_pack_words(bsw_streams sv, int first, const int64_t *__restrict__ offs, const int32_t *__restrict__ base,
+                             uint32_t *__restrict__ out, uint64_t *__restrict__ heads_out) {
     int b = blockIdx.x;
-    const uint32_t *src = sv.words + (int64_t)(first + b) * sv.cap;
-    int n = sv.nwords[first + b];
+    const int lo = base ? base[b] : 0;
+    const uint32_t *src = sv.words + (int64_t)(first + b) * sv.cap + lo;
+    int n = sv.nwords[first + b] - lo;
     uint32_t *dst = out + offs[b];
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     if (threadIdx.x == 0) heads_out[b] = sv.heads[first + b];
 }
-__global__ void k_unpack_words(bsw_streams sv, int first, const int64_t *__restrict__ offs, const uint32_t *__restrict__ in,
-                               const uint64_t *__restrict__ heads_in) {
+__global__ void k_unpack_words(bsw_streams sv, int first, const int64_t *__restrict__ offs, const int32_t *__restrict__ base,
+                               const uint32_t *__restrict__ in, const uint64_t *__restrict__ heads_in) {
     int b = blockIdx.x;
-    uint32_t *dst = sv.words + (int64_t)(first + b) * sv.cap;
+    const int lo = base ? base[b] : 0;
     int64_t o = offs[b];
     int n = (int)(offs[b + 1] - o);
+    if ((int64_t)lo + n > sv.cap) {                       // corrupt lengths must not write past the stream's row
+        if (threadIdx.x == 0) sv.flags[first + b] = BSW_E_OVERFLOW;
+        return;
+    }
+    uint32_t *dst = sv.words + (int64_t)(first + b) * sv.cap + lo;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = in[o + i];
     if (threadIdx.x == 0) {
-        sv.nwords[first + b] = n; sv.minwords[first + b] = n; sv.heads[first + b] = heads_in[b]; sv.flags[first + b] = 0;
+        sv.nwords[first + b] = lo + n; sv.minwords[first + b] = base ? lo : n; sv.heads[first + b] = heads_in[b]; sv.flags[first + b] = 0;
     }
+}
+static int pack_impl(bsw_streams *s, int first, int count, uint32_t *words_dev, int64_t *offsets_dev, uint64_t *heads_dev,
+                     int32_t *base_dev, void *stream) {
+    BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B && words_dev && offsets_dev && heads_dev, "bsw_streams_pack: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_pack_offsets<<<1, 1024, 0, st>>>(s->nwords + first, s->minwords + first, base_dev != nullptr, count, offsets_dev, base_dev);
+    BSW_LAUNCH_CHECK();
+    k_pack_words<<<count, 256, 0, st>>>(*s, first, offsets_dev, base_dev, words_dev, heads_dev);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
 }
 extern "C" int bsw_streams_pack(bsw_streams *s, int first, int count, uint32_t *words_dev, int64_t *offsets_dev,
                                 uint64_t *heads_dev, void *stream) {
-    BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B && words_dev && offsets_dev && heads_dev, "bsw_streams_pack: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    k_pack_offsets<<<1, 1024, 0, st>>>(s->nwords + first, count, offsets_dev);
-    BSW_LAUNCH_CHECK();
-    k_pack_words<<<count, 256, 0, st>>>(*s, first, offsets_dev, words_dev, heads_dev);
-    BSW_LAUNCH_CHECK();
-    return BSW_OK;
+    return pack_impl(s, first, count, words_dev, offsets_dev, heads_dev, nullptr, stream);
+}
+extern "C" int bsw_streams_pack_trimmed(bsw_streams *s, int first, int count, uint32_t *words_dev, int64_t *offsets_dev,
+                                        uint64_t *heads_dev, int32_t *base_dev, void *stream) {
+    BSW_REQUIRE(base_dev, "bsw_streams_pack_trimmed: base_dev is required");
+    return pack_impl(s, first, count, words_dev, offsets_dev, heads_dev, base_dev, stream);
 }
 extern "C" int bsw_streams_unpack(bsw_streams *s, int first, int count, const uint32_t *words_dev, const int64_t *offsets_dev,
                                   const uint64_t *heads_dev, void *stream) {
     BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B && words_dev && offsets_dev && heads_dev, "bsw_streams_unpack: bad arguments");
-    k_unpack_words<<<count, 256, 0, (cudaStream_t)stream>>>(*s, first, offsets_dev, words_dev, heads_dev);
+    k_unpack_words<<<count, 256, 0, (cudaStream_t)stream>>>(*s, first, offsets_dev, nullptr, words_dev, heads_dev);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+extern "C" int bsw_streams_unpack_trimmed(bsw_streams *s, int first, int count, const uint32_t *words_dev, const int64_t *offsets_dev,
+                                          const uint64_t *heads_dev, const int32_t *base_dev, void *stream) {
+    BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B && words_dev && offsets_dev && heads_dev && base_dev, "bsw_streams_unpack_trimmed: bad arguments");
+    k_unpack_words<<<count, 256, 0, (cudaStream_t)stream>>>(*s, first, offsets_dev, base_dev, words_dev, heads_dev);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
 }

@@ -695,7 +695,7 @@ static int abi_2p(bool pop, bsw_streams *s, int first, int count, const float *m
     if (mode != 0 && S >= 8 && bits >= 8 && bits <= 31) {
         void *m = (uint8_t *)scratch + ((bsw_rows_scratch_bytes(count, L) + 63) & ~(size_t)63);
         int n_aff = 0;
-        if (int rc = bsw_rows6_build_meta(endp, ers, L, S, m, &n_aff, st)) return rc;
+        if (int rc = bsw_rows6_build_meta(endp, ers, L, S, m, mode == 1 ? nullptr : &n_aff, st)) return rc;    // mode 1: no probe, no synchronise
         if (mode == 1 || n_aff == (ers == 0 ? 1 : (int)L)) meta = m;
     }
     const size_t sb = bsw_rows_scratch_bytes(count, L);

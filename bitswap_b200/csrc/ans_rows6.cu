@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int RW6 = 16;      // warps per CTA in phase A (one row index, 16 streams): 512 threads x <= 64 registers
+// warps per CTA in phase A (one row index, RW6 streams).  16 x 32 x 64 registers = half an SM's register file, so two of
+// these CTAs fill an SM, or one of them sits beside one k_conv_tc CTA; 12 warps leave the compiler 80 registers.
 constexpr int PW6 = 4;       // warps (= streams) per CTA in phase B
 
 // exact float64 pmf of bin k of the row (what the reference's tensor expression yields, cifar_compress.py:182-184)
@@ -35,6 +36,19 @@ __device__ __noinline__ double r6_exact_pmf(const double *__restrict__ e, int k,
 }
 __device__ __forceinline__ uint32_t r6_exact_pm(const double *__restrict__ e, int k, int S, double m, double s, double rs, double mult) {
     return __double2uint_rz(__dmul_rn(r6_exact_pmf(e, k, S, m, s, rs), mult));        // :29 trunc
+}
+// The rare path of the table kernel: everything it needs is re-derived from the kernel arguments, so that the hot loop
+// does not have to keep mu, sigma, 1/sigma, mult and the endpoint pointer alive in registers.
+struct R6Args {
+    const float *mu; int64_t mss; const float *sc; int64_t sss; const double *endp; int64_t ers; int S, bits, q;
+};
+__device__ __noinline__ double r6_slow_pmf(const R6Args &A, int64_t row, int si, int k) {
+    const double m = (double)A.mu[(int64_t)si * A.mss + row], s = (double)A.sc[(int64_t)si * A.sss + row];
+    return r6_exact_pmf(A.endp + row * A.ers, k, A.S, m, s, __ddiv_rn(1.0, s));
+}
+__device__ __forceinline__ uint32_t r6_slow_pm(const R6Args &A, int64_t row, int si, int k) {
+    const double mult = (double)(((int64_t)1 << A.bits) - ((int64_t)1 << A.q));
+    return __double2uint_rz(__dmul_rn(r6_slow_pmf(A, row, si, k), mult));             // :29 trunc
 }
 
 // ---- per-row metadata: least-effort affine fit through the first and last endpoint + its worst deviation ------------------
@@ -70,22 +84,23 @@ __global__ void k_row_meta(const double *__restrict__ endp, int64_t ers, int64_t
 // vstat (VERIFY builds only): [0] bins whose emitted integer differs from the exact function's, [1] worst
 // |screened - exact| scaled pmf of a bin that was trusted, in thousandths of that row's window (1000 = the error that
 // could flip a truncation), [2] bins checked, [3] bins that took the exact path.
-template <bool POP, bool VERIFY>
+template <bool POP, bool VERIFY, int RW6>
 __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int S, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const R6RowMeta *__restrict__ meta, int64_t mrs, const int16_t *__restrict__ sym, int bits, int q,
-        uint4 *__restrict__ pairs, uint32_t *__restrict__ bases, uint2 *__restrict__ fix, unsigned long long *vstat) {
+        uint4 *__restrict__ pairs, uint32_t *__restrict__ bases, uint2 *__restrict__ fix, unsigned long long *vstat, int zero) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = blockIdx.x;
     const int si = blockIdx.y * RW6 + warp;
     if (si >= count) return;
-    const double *e = endp + row * ers;
+    const R6Args A = {mu, mss, sc, sss, endp, ers, S, bits, q};
     const R6RowMeta M = meta[row * mrs];
-    const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];   // cifar_train.py:375-376 up-cast
-    const double rs = __ddiv_rn(1.0, s);
-    const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));                         // :28
-    const double mult2 = mult * 1048576.0;               // pmf in 2^-20 fixed point: < 2^51 for bits <= 31
-    const R6Plan pl = r6_plan(M, m, rs, S, bits);
+    const double mult2 = (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0;   // :28; pmf in 2^-20 fixed point: < 2^51
+    R6Plan pl;
+    {
+        const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];   // cifar_train.py:375-376 up-cast
+        pl = r6_plan(M, m, __ddiv_rn(1.0, s), S, bits);
+    }
     const int ks = pl.kl + lane * pl.m;
     const int ke = min(ks + pl.m, pl.kh);
     int sy = 0;
@@ -103,10 +118,12 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
         rho[0] = r6_exp_neg(pl.dt);
         rho[1] = __dmul_rn(rho[0], rho[0]);
         rho[2] = __dmul_rn(rho[1], rho[0]);
-        rho[3] = r6_exp_neg(4.0 * pl.dt);                 // the chain multiplier gets its own exp: its error is applied m/4 times
-        auto group = [&](int k0, auto last_t) {
+        rho[3] = __dmul_rn(rho[1], rho[1]);               // (chain multiplier: its ~6 ulp are applied m/4 <= 8 times -- measured < 3 of 64 window units)
+        // four registers that just hold `zero` (a kernel argument, so the compiler cannot fold it), see r6_rcp_seed_lo
+        const int zlo[4] = {zero, zero + zero, zero * 3, zero * 5};
+        auto group = [&](int k0, auto maybe_last_t, bool last) {
             double z[4];
-            r6_group<decltype(last_t)::value>(ub, prev, rho, mult2, pl.magic, z);
+            r6_group<decltype(maybe_last_t)::value>(ub, prev, rho, mult2, pl.magic, z, last, zlo);
             uint32_t vv[4];
             bool any = false;
 #pragma unroll
@@ -120,7 +137,7 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
             if (VERIFY) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const double ex = r6_exact_pmf(e, k0 + t, S, m, s, rs);
+                    const double ex = r6_slow_pmf(A, row, si, k0 + t);
                     if (pl.mask != 0u && !r6_doubt(z[t], pl.mask)) {
                         const double err = fabs((z[t] - pl.magic) - ex * mult2) * 1000.0 / (pl.magic - 6755399441055744.0);
                         atomicMax(vstat + 1, (unsigned long long)(err < 1e18 ? err + 0.999 : 1e18));
@@ -132,14 +149,14 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
                     if (r6_doubt(z[t], pl.mask)) {
-                        vv[t] = r6_exact_pm(e, k0 + t, S, m, s, rs, mult) + 0x80000000u;
+                        vv[t] = r6_slow_pm(A, row, si, k0 + t) + 0x80000000u;
                         if (VERIFY) atomicAdd(vstat + 3, 1ULL);
                     }
             }
             if (VERIFY) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    if (vv[t] != r6_exact_pm(e, k0 + t, S, m, s, rs, mult) + 0x80000000u) atomicAdd(vstat, 1ULL);
+                    if (vv[t] != r6_slow_pm(A, row, si, k0 + t) + 0x80000000u) atomicAdd(vstat, 1ULL);
             }
             const uint32_t gsum = (vv[0] + vv[1]) + (vv[2] + vv[3]);
             const uint32_t gmax = max(max(vv[0], vv[1]), max(vv[2], vv[3]));
@@ -160,10 +177,12 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
                 }
             }
         };
-        const int kend = min(ke, S - 4);
-#pragma unroll 1
-        for (int k0 = ks; k0 < kend; k0 += 4) group(k0, std::false_type{});
-        if (ke == S) group(S - 4, std::true_type{});      // the group holding bin S-1, whose upper cdf is the constant 1
+        // My last group is peeled for EVERY lane (no divergence): in the lane whose chunk ends the row it holds bin S-1,
+        // whose upper cdf is the constant 1 -- a select on one value instead of a second copy of the group for one lane.
+        const int klast = ke - 4;
+#pragma unroll 2
+        for (int k0 = ks; k0 < klast; k0 += 4) group(k0, std::false_type{}, false);
+        group(klast, std::true_type{}, ke == S);
         nbin = (uint32_t)(ke - ks);
     }
     int lbi = bestk;                                      // first position of the maximum inside its group
@@ -350,20 +369,21 @@ int g_verify = 0;
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------
 // meta_dev: L entries (or 1 when endp row stride is 0).  n_affine_host (may be NULL) receives the number of rows the
-// fast path applies to; synchronises `st` when it is given.
+// fast path applies to; the call synchronises `st` only when it is given.
 int bsw_rows6_build_meta(const double *endp, int64_t ers, int64_t L, int S, void *meta_dev, int *n_affine_host, cudaStream_t st) {
     BSW_REQUIRE(endp && meta_dev && L > 0 && S >= 8, "bsw_rows6_build_meta: bad arguments");
     const int64_t rows = ers == 0 ? 1 : L;
-    int *cnt = nullptr;
-    BSW_CUDA(cudaMalloc(&cnt, sizeof(int)));
+    static int *cnt = nullptr;                            // (one counter per process: only read back when the caller asks)
+    if (!cnt) BSW_CUDA(cudaMalloc(&cnt, sizeof(int)));
     BSW_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
     k_row_meta<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(endp, ers, rows, S, (R6RowMeta *)meta_dev, cnt);
     BSW_LAUNCH_CHECK();
-    int h = 0;
-    BSW_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BSW_CUDA(cudaStreamSynchronize(st));
-    cudaFree(cnt);
-    if (n_affine_host) *n_affine_host = h;
+    if (n_affine_host) {
+        int h = 0;
+        BSW_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BSW_CUDA(cudaStreamSynchronize(st));
+        *n_affine_host = h;
+    }
     return BSW_OK;
 }
 
@@ -383,15 +403,16 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
     uint32_t *bases = (uint32_t *)scratch;
     uint2 *fix = (uint2 *)((uint8_t *)scratch + (size_t)count * L * 128);
     if (phase == 0) {
-        dim3 grid((unsigned)L, (count + RW6 - 1) / RW6);
-        if (g_verify) {
-            if (!g_vstat) { BSW_CUDA(cudaMalloc(&g_vstat, 32)); BSW_CUDA(cudaMemset(g_vstat, 0, 32)); }
-            if (pop) k_rows6<true, true><<<grid, RW6 * 32, 0, st>>>(count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, nullptr, bits, q, nullptr, bases, fix, g_vstat);
-            else k_rows6<false, true><<<grid, RW6 * 32, 0, st>>>(count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, sym, bits, q, pairs, nullptr, nullptr, g_vstat);
-        } else {
-            if (pop) k_rows6<true, false><<<grid, RW6 * 32, 0, st>>>(count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, nullptr, bits, q, nullptr, bases, fix, nullptr);
-            else k_rows6<false, false><<<grid, RW6 * 32, 0, st>>>(count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, sym, bits, q, pairs, nullptr, nullptr, nullptr);
-        }
+        static const int env_w = getenv("BSW_R6_WARPS") ? atoi(getenv("BSW_R6_WARPS")) : 16;
+        if (g_verify && !g_vstat) { BSW_CUDA(cudaMalloc(&g_vstat, 32)); BSW_CUDA(cudaMemset(g_vstat, 0, 32)); }
+#define R6_LAUNCH(POP_, VER_, W_)                                                                                               \
+    k_rows6<POP_, VER_, W_><<<dim3((unsigned)L, (count + W_ - 1) / W_), W_ * 32, 0, st>>>(                                        \
+        count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, POP_ ? nullptr : sym, bits, q, POP_ ? nullptr : pairs,                 \
+        POP_ ? bases : nullptr, POP_ ? fix : nullptr, VER_ ? g_vstat : nullptr, 0)
+        if (g_verify) { if (pop) R6_LAUNCH(true, true, 16); else R6_LAUNCH(false, true, 16); }
+        else if (env_w == 12) { if (pop) R6_LAUNCH(true, false, 12); else R6_LAUNCH(false, false, 12); }
+        else { if (pop) R6_LAUNCH(true, false, 16); else R6_LAUNCH(false, false, 16); }
+#undef R6_LAUNCH
     } else {
         BSW_REQUIRE(pop, "affine coder: phase B of a push is k_push_pairs");
         k_pop6<<<(count + PW6 - 1) / PW6, PW6 * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, mt, mrs, bases, fix, sym, L, S, bits, q);

@@ -41,6 +41,7 @@ int bsw_ans_pop_i16(bsw_streams *s, int first, int count, const uint32_t *P, con
                     int16_t *sym, int64_t L, int S, int bits, cudaStream_t st);
 
 size_t bsw_rows_scratch_bytes(int count, int64_t L);
+int bsw_streams_mark_rest(bsw_streams *s, int first, int count, cudaStream_t st);
 int bsw_rows_mode();
 int bsw_prior_coarse(const uint32_t *C, int64_t L, int S, uint32_t *coarse, uint2 *fix, cudaStream_t st);
 int bsw_pop_shared_table(bsw_streams *s, int first, int count, const uint32_t *P, const uint32_t *coarse, const uint2 *fix,
@@ -342,6 +343,7 @@ extern "C" int bsw_codec_encode(bsw_codec *c, bsw_streams *s, int first, int cou
             if (zi == 0) RC(k.gather_x(x)); else RC(k.gather_z(zi - 1, zsym));           // :180
             RC(k.infer(zi));                                                                // :181
             RC(k.pop_z(zi, ztop));                                                          // :182-187
+            if (zi == 0) { RC(bsw_streams_mark_rest(s, first, count, k.st)); ++k.nl; }      // :190-192 restbits (first pop of a chain only)
             RC(k.gather_z(zi, ztop));                                                       // :195
             RC(k.generate(zi));                                                             // :196
             if (zi == 0) RC(k.push_x(c->xsym)); else RC(k.push_z(zi - 1, zsym));           // :197-202
@@ -354,6 +356,7 @@ extern "C" int bsw_codec_encode(bsw_codec *c, bsw_streams *s, int first, int cou
             if (zi == 0) RC(k.gather_x(x)); else RC(k.gather_z(zi - 1, c->zs[zi - 1]));
             RC(k.infer(zi));
             RC(k.pop_z(zi, c->zs[zi]));
+            if (zi == 0) { RC(bsw_streams_mark_rest(s, first, count, k.st)); ++k.nl; }      // :224-226 restbits
         }
         for (int zi = 0; zi < nz; ++zi) {
             RC(k.gather_z(zi, c->zs[zi]));

@@ -74,6 +74,59 @@ def gather_bitstreams(words, offsets, heads, device=None, group=None):
     return out
 
 
+def gather_packed(words_t, lens_t, heads_t, base_t=None, group=None):
+    """Device-resident gather of packed bitstreams: every rank contributes the tensors StreamSet.pack_device() returned
+    (words int32 [>= sum(lens)], lens int64 [s_r], heads int64 [s_r], base int32 [s_r] or None) and receives
+    (W [world, maxtot] int32, meta [world, 3, smax] int64 = lens / heads / base per rank, counts [world, 2] int64 =
+    (total words, streams) per rank) -- tensors on the input's device, nothing staged through the host.
+    Two collectives (+ one tiny one for the sizes): NCCL all_gather_into_tensor over NVLink on the GPU box, gloo in the
+    CPU tests.  With trimmed packing the payload is the PRODUCED words only (about 1-5 KB per image), which is what
+    SURVEY.md 8e budgets; the never-borrowed initial words stay home."""
+    world = dist.get_world_size(group)
+    dev = words_t.device
+    s_r = int(lens_t.numel())
+    total = lens_t.sum().reshape(1)
+    mine = torch.cat([total, torch.tensor([s_r], dtype=torch.int64, device=dev)])
+    counts = torch.empty((world, 2), dtype=torch.int64, device=dev)
+    _all_gather_into(counts, mine, group)
+    cmax = counts.max(dim=0).values.tolist()                  # the only host synchronisation: two integers
+    maxtot, smax = max(int(cmax[0]), 1), max(int(cmax[1]), 1)
+    send = torch.zeros(maxtot, dtype=torch.int32, device=dev)
+    n_mine = int(counts[dist.get_rank(group), 0])
+    send[:n_mine] = words_t[:n_mine]
+    W = torch.empty((world, maxtot), dtype=torch.int32, device=dev)
+    _all_gather_into(W, send, group)
+    meta = torch.zeros((3, smax), dtype=torch.int64, device=dev)
+    meta[0, :s_r] = lens_t
+    meta[1, :s_r] = heads_t
+    if base_t is not None:
+        meta[2, :s_r] = base_t.to(torch.int64)
+    M = torch.empty((world, 3, smax), dtype=torch.int64, device=dev)
+    _all_gather_into(M, meta, group)
+    return W, M, counts
+
+
+def _all_gather_into(out, inp, group=None):
+    """all_gather_into_tensor where the backend has it (NCCL), list all_gather otherwise (older gloo)."""
+    try:
+        dist.all_gather_into_tensor(out.view(-1), inp.contiguous().view(-1), group=group)
+    except (RuntimeError, NotImplementedError):
+        world = dist.get_world_size(group)
+        parts = [torch.empty_like(inp) for _ in range(world)]
+        dist.all_gather(parts, inp.contiguous(), group=group)
+        out.copy_(torch.stack(parts).view_as(out))
+
+
+def unpack_gathered(W, M, counts, rank):
+    """Rank `rank`'s slice of a gather_packed result as (words int32 [total], offsets int64 [s+1], heads int64 [s],
+    base int32 [s]) tensors, ready for StreamSet.unpack_device."""
+    total, s = int(counts[rank, 0]), int(counts[rank, 1])
+    lens = M[rank, 0, :s]
+    offs = torch.zeros(s + 1, dtype=torch.int64, device=W.device)
+    offs[1:] = torch.cumsum(lens, 0)
+    return W[rank, :total].contiguous(), offs, M[rank, 1, :s].contiguous(), M[rank, 2, :s].to(torch.int32).contiguous()
+
+
 def reduce_sum(value: float, device=None, group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device or torch.device("cpu"))
     dist.all_reduce(t, group=group)

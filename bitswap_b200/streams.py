@@ -88,6 +88,25 @@ class StreamSet:
         return n
 
     @_on_own_device
+    def rest_words(self):
+        """Word count right after the first pop of each chain (reference: len(restbits) - 1, cifar_compress.py:190-192)."""
+        n = np.zeros(self.n, dtype=np.int64)
+        check(lib().bsw_streams_rest_words(self._h, n.ctypes.data))
+        return n
+
+    def bit_accounting(self, initial_words: int, xdim: int, images_per_chain: int):
+        """The reference's per-chain bookkeeping (cifar_compress.py:253-259) from the current stream sizes:
+        net = totaladdedbits / (xdim * images)  with totaladdedbits = (len(state) - len(initialstate)) * 32,
+        cma = totalbits / (xdim * images)       with totalbits = (len(state) - (len(restbits) - 1)) * 32 -- the
+        cumulative average INCLUDING the initial bits the first pop consumed."""
+        n, _, _ = self.sizes()
+        rest = self.rest_words()
+        added = (n - int(initial_words)) * 32.0
+        total = (n + 1 - rest) * 32.0
+        return dict(net_bits_per_dim=added / (xdim * images_per_chain), cma_bits_per_dim=total / (xdim * images_per_chain),
+                    total_bits=total, total_added_bits=added)
+
+    @_on_own_device
     def export(self, first=0, count=None):
         """Packed export: (words uint32[sum], offsets int64[count+1], heads uint64[count], flags)."""
         count = self.n - first if count is None else count
@@ -109,6 +128,8 @@ class StreamSet:
             st = dict(words_d=torch.empty(need, dtype=torch.int32, device="cuda"),
                       offs_d=torch.empty(count + 1, dtype=torch.int64, device="cuda"),
                       heads_d=torch.empty(count, dtype=torch.int64, device="cuda"),
+                      base_d=torch.empty(count, dtype=torch.int32, device="cuda"),
+                      base_h=torch.empty(count, dtype=torch.int32).pin_memory(),
                       words_h=torch.empty(need, dtype=torch.int32).pin_memory(),
                       offs_h=torch.empty(count + 1, dtype=torch.int64).pin_memory(),
                       heads_h=torch.empty(count, dtype=torch.int64).pin_memory())
@@ -116,42 +137,77 @@ class StreamSet:
         return st
 
     @_on_own_device
-    def export_packed(self, first=0, count=None):
-        """(words uint32[sum], offsets int64[count+1], heads uint64[count]) as numpy views of pinned host buffers
-        (valid until the next export_packed/import_packed_fast).  Enqueued on torch's current stream; synchronises it."""
-        import torch
+    def pack_device(self, first=0, count=None, trim=False):
+        """Device-side gather of the streams' words into one contiguous buffer, async on torch's current stream.
+        Returns device tensors (words int32 [capacity view], offsets int64 [count+1], heads int64 [count],
+        base int32 [count] or None).  trim=True packs only words[base_b .. n_b): the part above the lowest depth each
+        stack ever reached (the untouched initial words below it are re-created by the receiver from the seed,
+        demo_compress.py:137,160)."""
         from ._lib import cuda_stream_ptr
         count = self.n - first if count is None else count
         st = self._staging(count)
-        check(lib().bsw_streams_pack(self._h, first, count, st["words_d"].data_ptr(), st["offs_d"].data_ptr(),
-                                     st["heads_d"].data_ptr(), cuda_stream_ptr()))
+        if trim:
+            check(lib().bsw_streams_pack_trimmed(self._h, first, count, st["words_d"].data_ptr(), st["offs_d"].data_ptr(),
+                                                 st["heads_d"].data_ptr(), st["base_d"].data_ptr(), cuda_stream_ptr()))
+        else:
+            check(lib().bsw_streams_pack(self._h, first, count, st["words_d"].data_ptr(), st["offs_d"].data_ptr(),
+                                         st["heads_d"].data_ptr(), cuda_stream_ptr()))
+        return st["words_d"], st["offs_d"][:count + 1], st["heads_d"][:count], (st["base_d"][:count] if trim else None)
+
+    @_on_own_device
+    def unpack_device(self, words_d, offs_d, heads_d, base_d=None, first=0):
+        """Inverse of pack_device from device tensors (e.g. what an NCCL gather delivered).  With base_d the streams must
+        already hold their initial words (fill / import): the packed words are written above base_b."""
+        from ._lib import cuda_stream_ptr
+        count = heads_d.numel()
+        if base_d is None:
+            check(lib().bsw_streams_unpack(self._h, first, count, words_d.data_ptr(), offs_d.data_ptr(), heads_d.data_ptr(), cuda_stream_ptr()))
+        else:
+            check(lib().bsw_streams_unpack_trimmed(self._h, first, count, words_d.data_ptr(), offs_d.data_ptr(), heads_d.data_ptr(),
+                                                   base_d.data_ptr(), cuda_stream_ptr()))
+
+    @_on_own_device
+    def export_packed(self, first=0, count=None, trim=False):
+        """(words uint32[sum], offsets int64[count+1], heads uint64[count][, base int32[count]]) as numpy views of pinned
+        host buffers (valid until the next export_packed/import_packed_fast).  Enqueued on torch's current stream;
+        synchronises it.  trim=True: see pack_device."""
+        import torch
+        count = self.n - first if count is None else count
+        st = self._staging(count)
+        self.pack_device(first, count, trim)
         st["offs_h"][:count + 1].copy_(st["offs_d"][:count + 1], non_blocking=True)
         st["heads_h"][:count].copy_(st["heads_d"][:count], non_blocking=True)
+        if trim:
+            st["base_h"][:count].copy_(st["base_d"][:count], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         total = int(st["offs_h"][count])
         st["words_h"][:total].copy_(st["words_d"][:total], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return (st["words_h"][:total].numpy().view(np.uint32), st["offs_h"][:count + 1].numpy(),
-                st["heads_h"][:count].numpy().view(np.uint64))
+        out = (st["words_h"][:total].numpy().view(np.uint32), st["offs_h"][:count + 1].numpy(),
+               st["heads_h"][:count].numpy().view(np.uint64))
+        return out + (st["base_h"][:count].numpy(),) if trim else out
 
     @_on_own_device
-    def import_packed_fast(self, words, offsets, heads, first=0):
+    def import_packed_fast(self, words, offsets, heads, first=0, base=None):
         """Inverse of export_packed (host arrays -> device scatter). Async on torch's current stream."""
         import torch
-        from ._lib import cuda_stream_ptr
         count = len(heads)
         total = int(offsets[count])
-        assert int(np.max(np.diff(offsets))) <= self.capacity
+        assert int(np.max(np.diff(offsets))) + (int(np.max(base)) if base is not None else 0) <= self.capacity
         st = self._staging(count)
         if words.ctypes.data != st["words_h"].data_ptr():
             st["words_h"][:total].copy_(torch.from_numpy(np.ascontiguousarray(words).view(np.int32)))
             st["offs_h"][:count + 1].copy_(torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)))
             st["heads_h"][:count].copy_(torch.from_numpy(np.ascontiguousarray(heads).view(np.int64)))
+            if base is not None:
+                st["base_h"][:count].copy_(torch.from_numpy(np.ascontiguousarray(base, dtype=np.int32)))
         st["words_d"][:total].copy_(st["words_h"][:total], non_blocking=True)
         st["offs_d"][:count + 1].copy_(st["offs_h"][:count + 1], non_blocking=True)
         st["heads_d"][:count].copy_(st["heads_h"][:count], non_blocking=True)
-        check(lib().bsw_streams_unpack(self._h, first, count, st["words_d"].data_ptr(), st["offs_d"].data_ptr(),
-                                       st["heads_d"].data_ptr(), cuda_stream_ptr()))
+        if base is not None:
+            st["base_d"][:count].copy_(st["base_h"][:count], non_blocking=True)
+        self.unpack_device(st["words_d"], st["offs_d"][:count + 1], st["heads_d"][:count],
+                           st["base_d"][:count] if base is not None else None, first)
 
     def export_lists(self, first=0, count=None):
         words, offs, heads, flags = self.export(first, count)

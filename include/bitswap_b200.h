@@ -73,6 +73,10 @@ int bsw_streams_sizes(bsw_streams *s, int64_t *nwords_host, uint64_t *heads_host
 /* Lowest word count each stream has reached since import/fill: the part of the initial random words that was never
  * borrowed and can be trimmed from a stored bitstream (demo_compress.py:137,160 `excess_state_len`). Synchronous. */
 int bsw_streams_min_words(bsw_streams *s, int64_t *min_host);
+/* Word count of each stream right after the FIRST pop of its chain since import/fill (-1: none yet): the reference's
+ * len(restbits) - 1, from which it reports `totalbits` and the cumulative moving average (cifar_compress.py:190-192,254,259).
+ * Recorded by bsw_codec_encode.  Synchronous. */
+int bsw_streams_rest_words(bsw_streams *s, int64_t *rest_host);
 /* Packed export: stream i's words go to words_host[offsets_host[i] ...). Synchronous. */
 int bsw_streams_export(bsw_streams *s, int first, int count, uint32_t *words_host, const int64_t *offsets_host);
 /* Device-side packed (de)serialisation, async on `stream`: all streams' words gathered into one contiguous device
@@ -82,6 +86,15 @@ int bsw_streams_pack(bsw_streams *s, int first, int count, uint32_t *words_dev, 
                      void *stream);
 int bsw_streams_unpack(bsw_streams *s, int first, int count, const uint32_t *words_dev, const int64_t *offsets_dev,
                        const uint64_t *heads_dev, void *stream);
+/* Trimmed forms: only words[base_b .. n_b) of every stream travel, base_b = the lowest depth the stack ever reached
+ * (bsw_streams_min_words) -- the initial random words below it were never borrowed and the receiver re-creates them from
+ * the seed (demo_compress.py:137,160; demo_decompress.py:176-186).  base_dev: int32 [count], written by pack, read by
+ * unpack.  unpack_trimmed writes above base_b into streams that already hold the initial words (bsw_streams_fill /
+ * import), and flags BSW_E_OVERFLOW instead of writing past a stream's capacity. */
+int bsw_streams_pack_trimmed(bsw_streams *s, int first, int count, uint32_t *words_dev, int64_t *offsets_dev,
+                             uint64_t *heads_dev, int32_t *base_dev, void *stream);
+int bsw_streams_unpack_trimmed(bsw_streams *s, int first, int count, const uint32_t *words_dev, const int64_t *offsets_dev,
+                               const uint64_t *heads_dev, const int32_t *base_dev, void *stream);
 /* Raw device views for device-resident pipelines (NCCL gathers, custom kernels). */
 int bsw_streams_device_ptrs(bsw_streams *s, uint32_t **words_dev, int32_t **nwords_dev, uint64_t **heads_dev,
                             int32_t **flags_dev);

@@ -332,8 +332,29 @@ class BitSwapOracle:
         self.coder_kind, self.pmf_kind, self.trace = coder, pmf, trace
         self.zr, self.xr = torch.arange(cfg.zdim), torch.arange(cfg.xdim)
         self.mu_hook = None     # optional: callable(kind, level, mu, scale) -> (mu, scale) to inject GPU nets
+        self.timers = None      # optional dict: seconds per phase {net, cdf, tables, pop, push} (bench.py's 5-way split)
 
     # -- helpers ------------------------------------------------------------------------------
+    def _timed(self, name, fn, *a):
+        if self.timers is None:
+            return fn(*a)
+        import time
+        t0 = time.perf_counter()
+        r = fn(*a)
+        self.timers[name] = self.timers.get(name, 0.0) + time.perf_counter() - t0
+        return r
+
+    def _pop(self, endpoints, mu, sc, q, state):
+        """tables + decode of one level: float64 pmfs (:182-184), ANS.__init__ (:13-46), ANS.decode (:57-67)."""
+        pm = self._timed("cdf", self._pmfs, endpoints, mu, sc)
+        coder = self._timed("tables", self._coder, pm, q)
+        return self._timed("pop", coder.decode, state)
+
+    def _push(self, endpoints, mu, sc, q, state, symbols):
+        pm = self._timed("cdf", self._pmfs, endpoints, mu, sc)
+        coder = self._timed("tables", self._coder, pm, q)
+        return self._timed("push", coder.encode, state, symbols)
+
     def _pmfs(self, endpoints, mu, scale):
         if self.pmf_kind == "torch":
             return logistic_pmfs_torch(endpoints, mu, scale).numpy()
@@ -349,6 +370,9 @@ class BitSwapOracle:
         return AnsPort(pmfs, bits, q) if self.coder_kind == "port" else AnsC(pmfs, bits, q)
 
     def _net(self, kind, level, given):
+        return self._timed("net", self._net_raw, kind, level, given)
+
+    def _net_raw(self, kind, level, given):
         f = self.model.infer(level) if kind == "infer" else self.model.generate(level)
         mu, sc = f(given.unsqueeze(0))
         mu, sc = mu[0], sc[0]
@@ -376,17 +400,16 @@ class BitSwapOracle:
         for zi in range(c.nz):
             given = self.zcen[zi - 1, self.zr, zsym] if zi > 0 else self.xcen[self.xr, x]           # :180
             mu, sc = self._net("infer", zi, given)                                                  # :181
-            state, zsymtop = self._coder(self._pmfs(self.zend[zi], mu, sc), q).decode(state)        # :182-187
+            state, zsymtop = self._pop(self.zend[zi], mu, sc, q, state)                             # :182-187
             zsymtop = torch.as_tensor(np.asarray(zsymtop))
             self._note(f"pop z{zi+1}", state)
             z = self.zcen[zi, self.zr, zsymtop]                                                     # :195
             mu, sc = self._net("generate", zi, z)                                                   # :196
             ends = self.zend[zi - 1] if zi > 0 else self.xend                                       # :197
-            state = self._coder(self._pmfs(ends, mu, sc), q if zi > 0 else 8).encode(               # :202
-                state, (zsym if zi > 0 else x).numpy())
+            state = self._push(ends, mu, sc, q if zi > 0 else 8, state, (zsym if zi > 0 else x).numpy())   # :202
             self._note(f"push {'z%d' % zi if zi > 0 else 'x'}", state)
             zsym = zsymtop                                                                          # :204
-        state = self._coder(self._prior(), q).encode(state, zsym.numpy())                           # :245-250
+        state = self._timed("push", self._timed("tables", self._coder, self._timed("cdf", self._prior), q).encode, state, zsym.numpy())   # :245-250
         self._note("push prior", state)
         return state
 
@@ -394,17 +417,17 @@ class BitSwapOracle:
     def decode_image(self, state):
         c = self.cfg
         q = c.quantbits
-        state, zsymtop = self._coder(self._prior(), q).decode(state)                                # :284-289
+        state, zsymtop = self._timed("pop", self._timed("tables", self._coder, self._timed("cdf", self._prior), q).decode, state)   # :284-289
         zsymtop = torch.as_tensor(np.asarray(zsymtop))
         for zi in reversed(range(c.nz)):                                                            # :294
             z = self.zcen[zi, self.zr, zsymtop]
             mu, sc = self._net("generate", zi, z)                                                   # :296-297
             ends = self.zend[zi - 1] if zi > 0 else self.xend
-            state, sym = self._coder(self._pmfs(ends, mu, sc), q if zi > 0 else 8).decode(state)    # :303
+            state, sym = self._pop(ends, mu, sc, q if zi > 0 else 8, state)                         # :303
             sym = torch.as_tensor(np.asarray(sym))
             given = self.zcen[zi - 1, self.zr, sym] if zi > 0 else self.xcen[self.xr, sym]          # :306
             mu, sc = self._net("infer", zi, given)                                                  # :307
-            state = self._coder(self._pmfs(self.zend[zi], mu, sc), q).encode(state, zsymtop.numpy())  # :313
+            state = self._push(self.zend[zi], mu, sc, q, state, zsymtop.numpy())                    # :313
             zsymtop = sym                                                                           # :315
         return state, zsymtop.numpy().astype(np.uint8)
 

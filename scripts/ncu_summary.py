@@ -2,6 +2,9 @@
 
   python scripts/ncu_summary.py launches <launches.csv> <out.md>     per-kernel time share of a launch list
   python scripts/ncu_summary.py full <report.ncu-rep> <out.md>       key metrics of a --set full capture
+  python scripts/ncu_summary.py facts <streams_per_launch> <out.json> <report.ncu-rep>...
+        per bench.py kernel category: dram bytes and FP64-pipe warp instructions per launch (what bench.py's
+        roofline.traffic / roofline.fp64 are taken from), averaged over the captured launches of that category
 """
 import csv
 import subprocess
@@ -61,5 +64,54 @@ def full(path, out):
                     f.write(f"| {k} | {r[hdr.index(k)]} | {units[hdr.index(k)]} |\n")
 
 
+CATS = [("rows_z", r"k_rows6?<", 2048), ("rows_x", r"k_rows6?<", 3072), ("pop_z", r"k_pop6|k_pop_coarse", None),
+        ("push_z", r"k_push_pairs", None), ("conv_dense3x3", r"k_conv_tc\b|k_conv_tc\(", None)]
+
+
+def facts(streams, out, paths):
+    import json
+    import re
+    acc = {}
+    for path in paths:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        hdr = rows[0]
+
+        def col(r, name, default=0.0):
+            return float(r[hdr.index(name)].replace(",", "")) if name in hdr and r[hdr.index(name)] else default
+        units = rows[1]
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")]
+            gx = int(col(r, "launch__grid_dim_x"))
+            for cat, rx, want_gx in CATS:
+                if not re.search(rx, name) or (want_gx is not None and gx != want_gx):
+                    continue
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                rd = col(r, "dram__bytes_read.sum") * scale.get(units[hdr.index("dram__bytes_read.sum")], 1.0)
+                wr = col(r, "dram__bytes_write.sum") * scale.get(units[hdr.index("dram__bytes_write.sum")], 1.0)
+                if "sm__inst_executed_pipe_fp64.sum" in hdr:
+                    f64 = col(r, "sm__inst_executed_pipe_fp64.sum")
+                    how = "sm__inst_executed_pipe_fp64.sum"
+                else:     # 2 FP64 warp instructions per SM and cycle at peak (4 sub-partitions x 16 lanes)
+                    f64 = col(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active") / 100.0 * 2.0 * col(r, "sm__cycles_active.avg") * 148
+                    how = "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active x 2/cycle/SM x sm__cycles_active.avg x 148 SMs"
+                a = acc.setdefault(cat, {"n": 0, "dram": 0.0, "f64": 0.0, "ms": 0.0, "inst": 0.0, "src": set(), "how": how})
+                a["n"] += 1; a["dram"] += rd + wr; a["f64"] += f64
+                a["ms"] += col(r, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")].replace("second", "s").replace("msecond", "ms").replace("usecond", "us").replace("nsecond", "ns"), 1.0)
+                a["inst"] += col(r, "smsp__inst_executed.sum")
+                a["src"].add(path)
+                break
+    res = {}
+    for cat, a in acc.items():
+        res[cat] = {"streams_per_launch": int(streams), "dram_bytes_per_launch": a["dram"] / a["n"], "fp64_inst_per_launch": a["f64"] / a["n"],
+                    "warp_inst_per_launch": a["inst"] / a["n"], "ncu_ms_per_launch": a["ms"] / a["n"], "launches_captured": a["n"],
+                    "fp64_count_from": a["how"], "source": ", ".join(sorted(a["src"]))}
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "facts":
+        facts(sys.argv[2], sys.argv[3], sys.argv[4:])
+        sys.exit(0)
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

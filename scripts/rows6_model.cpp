@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <vector>
 #include <algorithm>
+#include <string.h>
 #include "../bitswap_b200/csrc/rows6_core.cuh"
 
 static double rcp_fast(double d) {
@@ -33,7 +34,7 @@ int main(int argc, char **argv) {
     const int bits = 31;
     long mism = 0, deadbad = 0, popbad = 0, doubted = 0, bins = 0, evaluated = 0, notok = 0;
     double worst = 0;  // window units
-    double worst_frac = 0;
+    double worst_frac = 0, worst64 = 0;
     for (long it = 0; it < nrows; ++it) {
         int mode = it % 8;
         int S = (mode == 6) ? 256 : (mode == 7 ? 64 : 1024);
@@ -73,11 +74,11 @@ int main(int argc, char **argv) {
             if (ks >= ke) continue;
             double ub = r6_exp_neg(fma((double)(ks - 1), pl.dt, pl.t0));
             double prev = ks == 0 ? 0.0 : r6_rcp3(1.0 + ub);
-            double rho[4] = {r6_exp_neg(pl.dt), 0, 0, r6_exp_neg(4.0 * pl.dt)};
-            rho[1] = rho[0] * rho[0]; rho[2] = rho[1] * rho[0];
+            double rho[4] = {r6_exp_neg(pl.dt), 0, 0, 0};
+            rho[1] = rho[0] * rho[0]; rho[2] = rho[1] * rho[0]; rho[3] = rho[1] * rho[1];
             auto group = [&](int k0, bool last) {
                 double z[4];
-                if (last) r6_group<true>(ub, prev, rho, mult2, pl.magic, z); else r6_group<false>(ub, prev, rho, mult2, pl.magic, z);
+                r6_group<true>(ub, prev, rho, mult2, pl.magic, z, last, {0, 0, 0, 0});
                 uint32_t mn = 0xffffffffu; bool any = false; uint32_t vv[4];
                 for (int t = 0; t < 4; ++t) { uint32_t raw = r6_raw(z[t]); any |= r6_doubt(z[t], pl.mask); mn = std::min(mn, raw); vv[t] = raw + 0x80000001u; }
                 for (int t = 0; t < 4; ++t) {
@@ -87,6 +88,7 @@ int main(int argc, char **argv) {
                         worst = fmax(worst, err);
                         double win = pl.magic - 6755399441055744.0;
                         worst_frac = fmax(worst_frac, err / win);
+                        if (win == 64.0) worst64 = fmax(worst64, err);
                     }
                 }
                 if (any || mn < 0x80000000u) {
@@ -95,9 +97,9 @@ int main(int argc, char **argv) {
                 }
                 for (int t = 0; t < 4; ++t) { P[k0 + t] = vv[t]; lsum[lane] += vv[t]; }
             };
-            int kend = std::min(ke, S - 4);
-            for (int k0 = ks; k0 < kend; k0 += 4) group(k0, false);
-            if (ke == S) group(S - 4, true);
+            int klast = ke - 4;
+            for (int k0 = ks; k0 < klast; k0 += 4) group(k0, false);
+            group(klast, ke == S);
         }
         for (int k = 0; k < S; ++k) {
             ++bins;
@@ -127,6 +129,7 @@ int main(int argc, char **argv) {
         }
     }
     printf("rows %ld bins %ld evaluated %ld (%.1f%%) exact-path %ld (%.4f%% of evaluated) plan-not-ok %ld\n", nrows, bins, evaluated, 100.0 * evaluated / bins, doubted, 100.0 * doubted / evaluated, notok);
+    printf("worst trusted err among rows with the minimum window (64 units): %.2f units\n", worst64);
     printf("mismatches %ld (in dead zones %ld)  pop-search mismatches %ld  worst trusted err %.2f units (%.3f of its window)\n", mism, deadbad, popbad, worst, worst_frac);
     return (mism || popbad) ? 2 : 0;
 }

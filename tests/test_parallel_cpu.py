@@ -61,6 +61,19 @@ def _worker(rank, world, port, q):
         np.cumsum([s.n for s in states], out=offs[1:])
         heads = np.array([s.head for s in states], dtype=np.uint64)
         gathered = parallel.gather_bitstreams(words, offs, heads)
+        # the device-resident form (tensors in, tensors out; CPU tensors here): trimmed payload = words above `base`
+        base = np.array([min(s.n, 600 + 10 * i) for i, s in enumerate(states)], dtype=np.int32)
+        tw = np.concatenate([s.words[b0:s.n] for s, b0 in zip(states, base)]) if states else np.zeros(0, np.uint32)
+        tl = np.array([s.n - b0 for s, b0 in zip(states, base)], dtype=np.int64)
+        W, M, counts = parallel.gather_packed(torch.from_numpy(tw.view(np.int32)), torch.from_numpy(tl),
+                                              torch.from_numpy(heads.view(np.int64)), torch.from_numpy(base))
+        for r in range(world):
+            w_r, o_r, h_r = gathered[r]
+            pw, po, ph, pb = parallel.unpack_gathered(W, M, counts, r)
+            assert np.array_equal(ph.numpy().view(np.uint64), h_r)
+            for i in range(len(h_r)):
+                full = w_r[o_r[i]:o_r[i + 1]]
+                assert np.array_equal(pw[po[i]:po[i + 1]].numpy().view(np.uint32), full[int(pb[i]):])
         total_bits = parallel.reduce_sum(bits)
         slowest = parallel.reduce_max(float(rank + 1))
         ok = True
