@@ -302,6 +302,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="sub-batches coded concurrently on separate CUDA streams (1 = off)")
     ap.add_argument("--lane-size", type=int, default=0, help="streams per lane (0 = batch/lanes); the last lane takes the remainder")
+    ap.add_argument("--dual-stream", type=int, default=-1, help="codec stream mode (bsw_codec_set_dual_stream); -1 = library default")
     ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
     ap.add_argument("--crop-images", type=int, default=100)
     ap.add_argument("--hwc-quirk", action="store_true", help="crop: feed blocks as imagenetcrop_compress.py:130 does")
@@ -345,6 +346,8 @@ def main():
     codec = PipelinedCodec(cfg, sd, bins, B, lanes=lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size)
     two_phase = not args.fused_coder
     codec.set_two_phase(two_phase)
+    if args.dual_stream >= 0:
+        codec.set_dual_stream(args.dual_stream)
     INIT_WORDS = 4096
     ss = StreamSet(B, INIT_WORDS + 2048)
     w, head = synthetic.initial_words(INIT_WORDS, seed=100)

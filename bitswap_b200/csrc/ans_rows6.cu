@@ -37,18 +37,12 @@ __device__ __noinline__ double r6_exact_pmf(const double *__restrict__ e, int k,
 __device__ __forceinline__ uint32_t r6_exact_pm(const double *__restrict__ e, int k, int S, double m, double s, double rs, double mult) {
     return __double2uint_rz(__dmul_rn(r6_exact_pmf(e, k, S, m, s, rs), mult));        // :29 trunc
 }
-// The rare path of the table kernel: everything it needs is re-derived from the kernel arguments, so that the hot loop
-// does not have to keep mu, sigma, 1/sigma, mult and the endpoint pointer alive in registers.
-struct R6Args {
-    const float *mu; int64_t mss; const float *sc; int64_t sss; const double *endp; int64_t ers; int S, bits, q;
-};
-__device__ __noinline__ double r6_slow_pmf(const R6Args &A, int64_t row, int si, int k) {
-    const double m = (double)A.mu[(int64_t)si * A.mss + row], s = (double)A.sc[(int64_t)si * A.sss + row];
-    return r6_exact_pmf(A.endp + row * A.ers, k, A.S, m, s, __ddiv_rn(1.0, s));
-}
-__device__ __forceinline__ uint32_t r6_slow_pm(const R6Args &A, int64_t row, int si, int k) {
-    const double mult = (double)(((int64_t)1 << A.bits) - ((int64_t)1 << A.q));
-    return __double2uint_rz(__dmul_rn(r6_slow_pmf(A, row, si, k), mult));             // :29 trunc
+// The rare path of the table kernel: everything it needs is re-derived from its by-value arguments (registers, no stack
+// frame in the caller), so that the hot loop does not have to keep mu, sigma, 1/sigma, mult and the endpoint pointer alive.
+__device__ __noinline__ double r6_slow_pmf(const float *__restrict__ mu, int64_t mss, const float *__restrict__ sc, int64_t sss,
+                                           const double *__restrict__ endp, int64_t ers, int S, int64_t row, int si, int k) {
+    const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];
+    return r6_exact_pmf(endp + row * ers, k, S, m, s, __ddiv_rn(1.0, s));
 }
 
 // ---- per-row metadata: least-effort affine fit through the first and last endpoint + its worst deviation ------------------
@@ -81,46 +75,67 @@ __global__ void k_row_meta(const double *__restrict__ endp, int64_t ers, int64_t
 }
 
 // ---- phase A -------------------------------------------------------------------------------------------------------------
+// One warp = one stream x 32/LPR consecutive rows: LPR lanes share a row, and every lane walks CPL = 32/LPR of the row's 32
+// chunks one after the other (chunks j*CPL .. j*CPL+CPL-1 for lane j of the row).  A chunk is what rows6_core.cuh defines
+// it to be -- m consecutive live bins, anchored by its own exp() and walked with the geometric recurrence -- so the
+// integers do not depend on LPR; what LPR buys is that the per-row work (1/sigma, the plan, exp(-dt), the scan / argmax /
+// remnant epilogue: about as many instructions as a whole 32-bin chunk) is issued once per 32/LPR rows instead of once per
+// row.  LPR = 32 is the one-row-per-warp mapping of the first version of this kernel.
 // vstat (VERIFY builds only): [0] bins whose emitted integer differs from the exact function's, [1] worst
 // |screened - exact| scaled pmf of a bin that was trusted, in thousandths of that row's window (1000 = the error that
 // could flip a truncation), [2] bins checked, [3] bins that took the exact path.
-template <bool POP, bool VERIFY, int RW6>
-__global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int S, const float *__restrict__ mu, int64_t mss,
+template <bool POP, bool VERIFY, int LPR>
+__global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const R6RowMeta *__restrict__ meta, int64_t mrs, const int16_t *__restrict__ sym, int bits, int q,
         uint4 *__restrict__ pairs, uint32_t *__restrict__ bases, uint2 *__restrict__ fix, unsigned long long *vstat, int zero) {
+    constexpr int RPW = 32 / LPR;                         // rows per warp
+    constexpr int CPL = 32 / LPR;                         // chunks per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row = blockIdx.x;
-    const int si = blockIdx.y * RW6 + warp;
+    const int j = lane % LPR;                             // my position among the lanes of my row
+    const int si = blockIdx.y * 16 + warp;
     if (si >= count) return;
-    const R6Args A = {mu, mss, sc, sss, endp, ers, S, bits, q};
-    const R6RowMeta M = meta[row * mrs];
+    const bool valid = (int64_t)blockIdx.x * RPW + lane / LPR < L;
+    const int64_t row = valid ? (int64_t)blockIdx.x * RPW + lane / LPR : L - 1;   // (lanes past the end redo the last row, write nothing)
     const double mult2 = (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0;   // :28; pmf in 2^-20 fixed point: < 2^51
     R6Plan pl;
     {
+        const R6RowMeta M = meta[row * mrs];
         const double m = (double)mu[(int64_t)si * mss + row], s = (double)sc[(int64_t)si * sss + row];   // cifar_train.py:375-376 up-cast
         pl = r6_plan(M, m, __ddiv_rn(1.0, s), S, bits);
     }
-    const int ks = pl.kl + lane * pl.m;
-    const int ke = min(ks + pl.m, pl.kh);
     int sy = 0;
     if (!POP) sy = (int)sym[(int64_t)si * L + row];
+    auto slow_raw = [&](int k) -> uint32_t {              // the exact function's integer, raw domain
+        const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));
+        return __double2uint_rz(__dmul_rn(r6_slow_pmf(mu, mss, sc, sss, endp, ers, S, row, si, k), mult)) + 0x80000000u;   // :29 trunc
+    };
 
     // Everything inside the loop stays in the "raw" domain: raw = 2^31 + trunc(pmf * mult) (the magic bit on top), which
     // orders like P = trunc + 1 (:29, :32) and sums to it modulo 2^32 once 1 - 2^31 per bin is added back at the end.
     uint32_t rsum = 0, lbest = 0, pre = 0, pv = 0, npre = 0, nbin = 0;
     uint32_t bestv[4] = {0u, 0u, 0u, 0u};
     int bestk = 0;
-    if (ks < ke) {
-        double ub = r6_exp_neg(__fma_rn((double)(ks - 1), pl.dt, pl.t0));       // exp(-t) at the endpoint below my first bin
+    uint32_t cpre[CPL];                                   // P-sum of my bins before chunk i (for the chunk bases of the pop side)
+    double rho[4];
+    rho[0] = r6_exp_neg(pl.dt);
+    rho[1] = __dmul_rn(rho[0], rho[0]);
+    rho[2] = __dmul_rn(rho[1], rho[0]);
+    rho[3] = __dmul_rn(rho[1], rho[1]);                   // (chain multiplier: its ~6 ulp are applied m/4 <= 8 times -- measured < 3 of 64 window units)
+    // four registers that just hold `zero` (a kernel argument, so the compiler cannot fold it), see r6_rcp_seed_lo
+    const int zlo[4] = {zero, zero + zero, zero * 3, zero * 5};
+#pragma unroll 1
+    for (int ci = 0; ci < CPL; ++ci) {
+        if (POP) {
+            const uint32_t sofar = rsum - nbin * 0x7fffffffu;
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) if (t == ci) cpre[t] = sofar;
+        }
+        const int ks = pl.kl + (j * CPL + ci) * pl.m;
+        const int ke = min(ks + pl.m, pl.kh);
+        if (ks >= ke) continue;
+        double ub = r6_exp_neg(__fma_rn((double)(ks - 1), pl.dt, pl.t0));       // exp(-t) at the endpoint below the chunk's first bin
         double prev = ks == 0 ? 0.0 : r6_rcp3(__dadd_rn(1.0, ub));               // lower edge of bin 0 is cdf = 0 (:184)
-        double rho[4];
-        rho[0] = r6_exp_neg(pl.dt);
-        rho[1] = __dmul_rn(rho[0], rho[0]);
-        rho[2] = __dmul_rn(rho[1], rho[0]);
-        rho[3] = __dmul_rn(rho[1], rho[1]);               // (chain multiplier: its ~6 ulp are applied m/4 <= 8 times -- measured < 3 of 64 window units)
-        // four registers that just hold `zero` (a kernel argument, so the compiler cannot fold it), see r6_rcp_seed_lo
-        const int zlo[4] = {zero, zero + zero, zero * 3, zero * 5};
         auto group = [&](int k0, auto maybe_last_t, bool last) {
             double z[4];
             r6_group<decltype(maybe_last_t)::value>(ub, prev, rho, mult2, pl.magic, z, last, zlo);
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
             if (VERIFY) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const double ex = r6_slow_pmf(A, row, si, k0 + t);
+                    const double ex = r6_slow_pmf(mu, mss, sc, sss, endp, ers, S, row, si, k0 + t);
                     if (pl.mask != 0u && !r6_doubt(z[t], pl.mask)) {
                         const double err = fabs((z[t] - pl.magic) - ex * mult2) * 1000.0 / (pl.magic - 6755399441055744.0);
                         atomicMax(vstat + 1, (unsigned long long)(err < 1e18 ? err + 0.999 : 1e18));
@@ -149,14 +164,14 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
                     if (r6_doubt(z[t], pl.mask)) {
-                        vv[t] = r6_slow_pm(A, row, si, k0 + t) + 0x80000000u;
+                        vv[t] = slow_raw(k0 + t);
                         if (VERIFY) atomicAdd(vstat + 3, 1ULL);
                     }
             }
             if (VERIFY) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    if (vv[t] != r6_slow_pm(A, row, si, k0 + t) + 0x80000000u) atomicAdd(vstat, 1ULL);
+                    if (vv[t] != slow_raw(k0 + t)) atomicAdd(vstat, 1ULL);
             }
             const uint32_t gsum = (vv[0] + vv[1]) + (vv[2] + vv[3]);
             const uint32_t gmax = max(max(vv[0], vv[1]), max(vv[2], vv[3]));
@@ -166,9 +181,11 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
 #pragma unroll
                 for (int t = 0; t < 4; ++t) bestv[t] = vv[t];
             }
-            if (!POP) {                                   // sy is the same in every lane: warp-uniform branches
-                if (k0 + 4 <= sy) { pre += gsum; npre += 4u; }
-                else if (k0 <= sy) {
+            if (!POP) {                                   // sy differs between the rows of a warp: selects, and one rare branch per row
+                const bool below = k0 + 4 <= sy;
+                pre += below ? gsum : 0u;
+                npre += below ? 4u : 0u;
+                if (!below && k0 <= sy) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         if (k0 + t < sy) { pre += vv[t]; ++npre; }
@@ -177,13 +194,13 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
                 }
             }
         };
-        // My last group is peeled for EVERY lane (no divergence): in the lane whose chunk ends the row it holds bin S-1,
-        // whose upper cdf is the constant 1 -- a select on one value instead of a second copy of the group for one lane.
+        // The chunk's last group is peeled for EVERY lane (no divergence): in the chunk that ends the row it holds bin S-1,
+        // whose upper cdf is the constant 1 -- a select on one value instead of a second copy of the group.
         const int klast = ke - 4;
 #pragma unroll 2
         for (int k0 = ks; k0 < klast; k0 += 4) group(k0, std::false_type{}, false);
         group(klast, std::true_type{}, ke == S);
-        nbin = (uint32_t)(ke - ks);
+        nbin += (uint32_t)(ke - ks);
     }
     int lbi = bestk;                                      // first position of the maximum inside its group
 #pragma unroll
@@ -191,36 +208,67 @@ __global__ void __launch_bounds__(RW6 * 32, 2) k_rows6(int count, int64_t L, int
     // back to P = trunc + 1: every bin carries 2^31 - 1 too much
     const uint32_t lsum = rsum - nbin * 0x7fffffffu;
     pre -= npre * 0x7fffffffu;
+    const bool have_pv = pv != 0u;                        // (raw values carry the 2^31 bit: never 0)
     pv -= 0x7fffffffu;
     lbest = nbin ? lbest - 0x7fffffffu : 0u;
     uint32_t incl = lsum;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, o, LPR);
+        if (j >= o) incl += t;
     }
     // dead bins carry P = 1 each (trunc(...) = 0, +1)
-    const uint32_t total = (uint32_t)pl.kl + __shfl_sync(FULL, incl, 31) + (uint32_t)(S - pl.kh);
-    // :35 first maximum of the row: chunks ascend with the lane, so it is the lowest lane that holds the row maximum
-    const uint32_t rowmax = __reduce_max_sync(FULL, lbest);
-    const int wl = __ffs(__ballot_sync(FULL, lbest == rowmax)) - 1;
-    const int bi = __shfl_sync(FULL, lbi, wl);
+    const uint32_t total = (uint32_t)pl.kl + __shfl_sync(FULL, incl, LPR - 1, LPR) + (uint32_t)(S - pl.kh);
+    // :35 first maximum of the row: chunks ascend with the lane, so it is the lowest lane of the row that holds the row maximum
+    uint32_t rowmax = lbest;
+    int bi = lbi;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) {
+        const uint32_t ov = __shfl_xor_sync(FULL, rowmax, o, LPR);
+        const int ok = __shfl_xor_sync(FULL, bi, o, LPR);
+        const bool other_lower = (j & o) != 0;            // my partner is a lower lane: it wins ties
+        if (ov > rowmax || (ov == rowmax && other_lower)) { rowmax = ov; bi = ok; }
+    }
     const uint32_t rem = (1u << bits) - total;
     const int64_t out = (int64_t)si * L + row;
     const uint32_t excl = (uint32_t)pl.kl + incl - lsum;  // integer cdf at my first bin, before the remnant
     if (POP) {
-        bases[out * 32 + lane] = excl + ((ks > bi) ? rem : 0u);
-        if (lane == 0)
-            fix[out] = make_uint2((uint32_t)bi | ((uint32_t)(pl.kl >> 2) << 10) | ((uint32_t)(pl.kh >> 2) << 18) | ((uint32_t)(pl.m >> 2) << 27), rem);
+        uint32_t bs[CPL];
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+            const int ks = pl.kl + (j * CPL + t) * pl.m;
+            bs[t] = excl + cpre[t] + ((ks > bi) ? rem : 0u);      // (an empty chunk gets the cdf at kh: above any m the search sends here)
+        }
+        if (valid) {
+            uint32_t *bo = bases + out * 32 + j * CPL;
+            if constexpr (CPL % 4 == 0) {
+#pragma unroll
+                for (int t = 0; t < CPL; t += 4) *reinterpret_cast<uint4 *>(bo + t) = make_uint4(bs[t], bs[t + 1], bs[t + 2], bs[t + 3]);
+            } else if constexpr (CPL == 2) {
+                *reinterpret_cast<uint2 *>(bo) = make_uint2(bs[0], bs[1]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) bo[t] = bs[t];
+            }
+            if (j == 0)
+                fix[out] = make_uint2((uint32_t)bi | ((uint32_t)(pl.kl >> 2) << 10) | ((uint32_t)(pl.kh >> 2) << 18) | ((uint32_t)(pl.m >> 2) << 27), rem);
+        }
     } else {
-        const uint32_t own = __ballot_sync(FULL, ks <= sy && sy < ke);
-        uint32_t cb, pb;
-        if (own) {
-            const int owner = __ffs(own) - 1;
-            cb = __shfl_sync(FULL, excl + pre, owner);
-            pb = __shfl_sync(FULL, pv, owner);
-        } else if (sy < pl.kl) { cb = (uint32_t)sy; pb = 1u; }
-        else { cb = total - (uint32_t)(S - sy); pb = 1u; }
-        if (lane == 0) {
+        // the row's C_s and P_s: sums over the row's lanes (one lane holds pv; every lane holds its share of the prefix)
+        uint32_t cb = pre, pb = have_pv ? pv : 0u;
+        uint32_t got = have_pv ? 1u : 0u;
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) {
+            cb += __shfl_xor_sync(FULL, cb, o, LPR);
+            pb += __shfl_xor_sync(FULL, pb, o, LPR);
+            got += __shfl_xor_sync(FULL, got, o, LPR);
+        }
+        cb += (uint32_t)pl.kl;
+        if (!got) {
+            if (sy < pl.kl) { cb = (uint32_t)sy; pb = 1u; }
+            else { cb = total - (uint32_t)(S - sy); pb = 1u; }
+        }
+        if (j == 0 && valid) {
             const uint32_t pf = pb + (bi == sy ? rem : 0u);
             const uint64_t Mg = pf == 1u ? ~0ull : ~0ull / (uint64_t)pf;          // reciprocal for the serial phase's division
             if ((unsigned)sy >= (unsigned)S) pairs[out] = make_uint4(0u, 0u, 0u, 0u);    // out-of-range symbol: flagged by the serial phase
@@ -364,6 +412,7 @@ __global__ void __launch_bounds__(PW6 * 32) k_pop6(bsw_streams sv, int first, in
 
 unsigned long long *g_vstat = nullptr;                   // device [4], allocated on first use of the VERIFY build
 int g_verify = 0;
+int g_lpr = 0;                                           // lanes per row of k_rows6 (0: BSW_R6_LPR or the default 4)
 
 }  // namespace
 
@@ -403,15 +452,21 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
     uint32_t *bases = (uint32_t *)scratch;
     uint2 *fix = (uint2 *)((uint8_t *)scratch + (size_t)count * L * 128);
     if (phase == 0) {
-        static const int env_w = getenv("BSW_R6_WARPS") ? atoi(getenv("BSW_R6_WARPS")) : 16;
+        // BSW_R6_LPR = lanes per row (32, 8, 4 or 2; default 4 = eight rows per warp): same integers, different mapping (A/B runs)
+        static const int env_lpr0 = getenv("BSW_R6_LPR") ? atoi(getenv("BSW_R6_LPR")) : 4;
+        const int env_lpr = g_lpr > 0 ? g_lpr : env_lpr0;
         if (g_verify && !g_vstat) { BSW_CUDA(cudaMalloc(&g_vstat, 32)); BSW_CUDA(cudaMemset(g_vstat, 0, 32)); }
-#define R6_LAUNCH(POP_, VER_, W_)                                                                                               \
-    k_rows6<POP_, VER_, W_><<<dim3((unsigned)L, (count + W_ - 1) / W_), W_ * 32, 0, st>>>(                                        \
+#define R6_LAUNCH(POP_, VER_, LPR_)                                                                                             \
+    k_rows6<POP_, VER_, LPR_><<<dim3((unsigned)((L + 32 / LPR_ - 1) / (32 / LPR_)), (count + 15) / 16), 512, 0, st>>>(            \
         count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, POP_ ? nullptr : sym, bits, q, POP_ ? nullptr : pairs,                 \
         POP_ ? bases : nullptr, POP_ ? fix : nullptr, VER_ ? g_vstat : nullptr, 0)
-        if (g_verify) { if (pop) R6_LAUNCH(true, true, 16); else R6_LAUNCH(false, true, 16); }
-        else if (env_w == 12) { if (pop) R6_LAUNCH(true, false, 12); else R6_LAUNCH(false, false, 12); }
-        else { if (pop) R6_LAUNCH(true, false, 16); else R6_LAUNCH(false, false, 16); }
+#define R6_PICK(VER_, LPR_) do { if (pop) R6_LAUNCH(true, VER_, LPR_); else R6_LAUNCH(false, VER_, LPR_); } while (0)
+        if (g_verify) { if (env_lpr == 32) R6_PICK(true, 32); else R6_PICK(true, 4); }
+        else if (env_lpr == 32) R6_PICK(false, 32);
+        else if (env_lpr == 8) R6_PICK(false, 8);
+        else if (env_lpr == 2) R6_PICK(false, 2);
+        else R6_PICK(false, 4);
+#undef R6_PICK
 #undef R6_LAUNCH
     } else {
         BSW_REQUIRE(pop, "affine coder: phase B of a push is k_push_pairs");
@@ -423,6 +478,11 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
 
 // Debug switch: 1 = every k_rows6 launch also evaluates the exact function for every bin and counts disagreements
 // (slow; tests/test_ans_gpu.py runs a full-size level through it).  Read + reset the counters with bsw_rows6_verify_read.
+extern "C" int bsw_rows6_set_lanes_per_row(int lpr) {
+    BSW_REQUIRE(lpr == 0 || lpr == 2 || lpr == 4 || lpr == 8 || lpr == 32, "bsw_rows6_set_lanes_per_row: 0 (default), 2, 4, 8 or 32");
+    g_lpr = lpr;
+    return BSW_OK;
+}
 extern "C" int bsw_rows6_set_verify(int on) { g_verify = on ? 1 : 0; return BSW_OK; }
 extern "C" int bsw_rows6_verify_read(uint64_t *out4_host) {
     BSW_REQUIRE(out4_host, "null argument");

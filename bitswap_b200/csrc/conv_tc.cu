@@ -77,10 +77,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a mis-programmed TMA/MMA must not hang the GPU -- trap instead (surfaces as a CUDA error).
+// The bound is wall time (2 s on %globaltimer, sampled every 2^14 failed polls), not a spin count: a time-sliced or
+// preempted context makes honest waits arbitrarily long in spins but not in device time spent inside this kernel.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if ((++spins & 0x3fffu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -523,6 +531,182 @@ k_conv_tc_h(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__
     }
 }
 
+// Persistent variant: ONE CTA per SM walks half-image tiles (128 pixels x 128 output channels) of the whole batch.
+//   * TMEM ping-pong: tile i accumulates into columns [256*(i&1), +256) (main 128 + cross 128) while the eight epilogue
+//     warps drain tile i-1 from the other 256 -- the epilogue (a third of k_conv_tc's CTA life on the 3x3 convs, nearly
+//     all of it on the in-convs) disappears under the next tile's MMAs, and the TMA ring keeps prefetching across tile
+//     boundaries, so the per-CTA start-up latency (allocation, tensormap fetch, first TMA round trip) is paid once per SM
+//     instead of once per tile.
+//   * Because the grid is at most one CTA per SM and every CTA is resident from the start, the block scheduler is free
+//     to place other streams' kernels (the FP64-bound coder kernels of another lane: 32 K registers, no shared memory)
+//     on the same SMs while the convolution runs -- with per-tile grids the queue of conv CTAs keeps them out.
+//   * k-block order, MMA order per accumulator and the epilogue arithmetic are those of k_conv_tc / k_conv_tc_h: results
+//     are bit-identical to both.
+constexpr int P_NSTAGE = 5;
+constexpr int P_SCRATCH = 8 * 32 * 36 * 4;   // one 32 x 36 float transposition tile per epilogue warp
+constexpr int P_SMEM_BYTES = P_NSTAGE * H_STAGE_BYTES + P_SCRATCH + 1024 + 256;
+
+// (min-blocks 2 only caps the registers at 96 per thread so that a 32 K-register coder CTA fits beside this one)
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_conv_tc_p(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
+            const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a, int ntiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float *scratch = reinterpret_cast<float *>(smem + P_NSTAGE * H_STAGE_BYTES);
+    uint64_t *full_bar = (uint64_t *)(smem + P_NSTAGE * H_STAGE_BYTES + P_SCRATCH);
+    uint64_t *empty_bar = full_bar + P_NSTAGE;
+    uint64_t *accf_bar = empty_bar + P_NSTAGE;           // [2] accumulator buffer complete (MMA -> epilogue)
+    uint64_t *acce_bar = accf_bar + 2;                   // [2] accumulator buffer drained  (epilogue -> MMA)
+    uint32_t *tmem_ptr = (uint32_t *)(acce_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = a.taps * a.cchunks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_lo) : "memory");
+        for (int s = 0; s < P_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&accf_bar[b], 1); mbar_init(&acce_bar[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {     // all 512 TMEM columns: two {main, cross} accumulator pairs
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // tile t -> image t>>2, output-channel half (t>>1)&1, pixel half t&1: the four tiles of an image run on neighbouring
+    // SMs at about the same time, so the activation planes they share come out of L2.
+    if (warp == 0) {
+        if (lane == 0) {     // ===== TMA producer =====
+            const int r = a.ks / 2;
+            int stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int img = t >> 2, co0 = ((t >> 1) & 1) * BN, mh = t & 1;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    int tap = kb / a.cchunks, c0 = (kb - tap * a.cchunks) * BK;
+                    int dy = tap / a.ks, dx = tap - dy * a.ks;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * H_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], H_STAGE_BYTES);
+                    tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r + 8 * mh, img);
+                    tma_load_4d(st + H_TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r + 8 * mh, img);
+                    tma_load_3d(st + 2 * H_TILE_BYTES, &wmap_hi, &full_bar[stage], c0, co0, tap);
+                    tma_load_3d(st + 2 * H_TILE_BYTES + WTILE_BYTES, &wmap_lo, &full_bar[stage], c0, co0, tap);
+                    if (++stage == P_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {     // ===== MMA issuer =====
+            int stage = 0, phase = 0, it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acce_bar[buf], ((it >> 1) & 1) ^ 1);      // the epilogue has drained this buffer (first use: passes)
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + buf * 256, d_cross = d_main + BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    uint32_t sbase = smem_u32(smem + stage * H_STAGE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        uint64_t a_hi = make_desc_sw64(sbase + kk * 32);
+                        uint64_t a_lo = make_desc_sw64(sbase + H_TILE_BYTES + kk * 32);
+                        uint64_t b_hi = make_desc_sw64(sbase + 2 * H_TILE_BYTES + kk * 32);
+                        uint64_t b_lo = make_desc_sw64(sbase + 2 * H_TILE_BYTES + WTILE_BYTES + kk * 32);
+                        umma_bf16(d_main, a_hi, b_hi, (kb | kk) != 0);
+                        umma_bf16(d_cross, a_lo, b_hi, (kb | kk) != 0);
+                        umma_bf16(d_cross, a_hi, b_lo, 1);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == P_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&accf_bar[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue (the coalesced one of k_conv_tc_h): warp w may read TMEM lanes 32*(w%4)..; the two warps of a
+        // quadrant split the 128 columns =====
+        const int ew = warp - 2;
+        const int chalf = ew >> 2;
+        const int quad = warp & 3;
+        float *tile = scratch + ew * (32 * 36);
+        const int rsub = lane >> 3, col4 = (lane & 7) * 4;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int img = t >> 2, co0 = ((t >> 1) & 1) * BN, mh = t & 1;
+            const int buf = it & 1;
+            mbar_wait(&accf_bar[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tb = tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int cc = chalf * 64; cc < chalf * 64 + 64; cc += 32) {
+                const int c0 = co0 + cc;
+                {
+                    uint32_t rr[32], rc[32];
+                    tmem_ld32(tb + cc, rr);
+                    tmem_ld32(tb + BN + cc, rc);
+                    if (cc == chalf * 64 + 32) {          // my last TMEM read of this tile: hand the buffer back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acce_bar[buf])) : "memory");
+                    }
+                    float4 *trow = reinterpret_cast<float4 *>(tile + lane * 36);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        trow[i] = make_float4(__uint_as_float(rr[4 * i]) + __uint_as_float(rc[4 * i]),
+                                              __uint_as_float(rr[4 * i + 1]) + __uint_as_float(rc[4 * i + 1]),
+                                              __uint_as_float(rr[4 * i + 2]) + __uint_as_float(rc[4 * i + 2]),
+                                              __uint_as_float(rr[4 * i + 3]) + __uint_as_float(rc[4 * i + 3]));
+                }
+                __syncwarp();
+                const float4 bq = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + col4));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 4 * k + rsub;
+                    const int64_t prow = ((int64_t)img * 256 + mh * 128 + quad * 32 + r) * 256 + c0 + col4;
+                    float4 x = *reinterpret_cast<const float4 *>(tile + r * 36 + col4);
+                    x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;      // same order as the direct path: (main+cross)+bias
+                    if (a.resid) {
+                        const float4 q = *reinterpret_cast<const float4 *>(a.resid + prow);
+                        x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+                    }
+                    if (a.T_elu) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+                    if (a.T) *reinterpret_cast<float4 *>(a.T + prow) = x;
+                    if (a.A_hi) {
+                        float y[4] = {x.x, x.y, x.z, x.w};
+                        uint32_t hi[2], lo[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float x0 = a.A_elu ? elu1(y[2 * i]) : y[2 * i], x1 = a.A_elu ? elu1(y[2 * i + 1]) : y[2 * i + 1];
+                            __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                            __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        *reinterpret_cast<uint2 *>(a.A_hi + prow) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2 *>(a.A_lo + prow) = make_uint2(lo[0], lo[1]);
+                    }
+                }
+                __syncwarp();                             // the tile is rewritten by the next chunk
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // float32 NHWC -> bf16 hi/lo planes (used once per net, after the SIMT in-conv)
 __global__ void k_split_planes(const float *__restrict__ in, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -657,6 +841,7 @@ int bsw_model_tc_prepare(bsw_model *m) {
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     m->tc_ready = true;
     return BSW_OK;
 }
@@ -689,6 +874,32 @@ int bsw_tc_split(bsw_model *m, const float *in, int which, int64_t n, cudaStream
     return BSW_OK;
 }
 
+// Persistent kernel (k_conv_tc_p) is the default for every tensor-core conv; BSW_TC_PERSIST=0 selects the per-tile grids
+// (A/B runs, identical results).  Grid = one CTA per SM of the current device (BSW_TC_PGRID overrides), at most one per tile.
+static int g_tc_mode = -1;
+static bool tc_persistent() {
+    static const bool on = !(getenv("BSW_TC_PERSIST") && getenv("BSW_TC_PERSIST")[0] == '0');
+    return g_tc_mode < 0 ? on : g_tc_mode == 1;
+}
+extern "C" int bsw_set_conv_mode(int mode) {
+    BSW_REQUIRE(mode >= -1 && mode <= 1, "bsw_set_conv_mode: -1 (default), 0 (per-tile grids) or 1 (persistent)");
+    g_tc_mode = mode;
+    return BSW_OK;
+}
+static unsigned tc_pgrid(int ntiles) {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        static const int env = getenv("BSW_TC_PGRID") ? atoi(getenv("BSW_TC_PGRID")) : 0;
+        sms[dev] = env > 0 ? env : (v > 0 ? v : 148);
+    }
+    return (unsigned)(ntiles < sms[dev] ? ntiles : sms[dev]);
+}
+
 // a.in must be one of the plane buffers: a.in_planes = 0/1 selects it; outputs a.A_planes = 0/1/-1.
 int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st) {
     TcState *ts = (TcState *)m->tc_state;
@@ -709,7 +920,10 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     // B=1024 -- the MMAs already run at the sustained bf16 rate, so hiding the epilogue buys nothing and the re-fetched
     // weight tiles cost the 5x5.  Full tile stays the default here; BSW_TC_HALFTILE=1 selects the other one.
     static const bool half_tile = getenv("BSW_TC_HALFTILE") && getenv("BSW_TC_HALFTILE")[0] == '1';
-    if (!use_cluster && half_tile)
+    if (!use_cluster && !half_tile && tc_persistent())
+        k_conv_tc_p<<<tc_pgrid((int)n * 4), TC_THREADS, P_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
+                                                                           s.map_hi, s.map_lo, t, (int)n * 4);
+    else if (!use_cluster && half_tile)
         k_conv_tc_h<true><<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
                                                                                    s.map_hi, s.map_lo, t);
     else if (use_cluster)
@@ -739,7 +953,9 @@ int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
     static const bool full_tile = getenv("BSW_TC_FULLTILE") && getenv("BSW_TC_FULLTILE")[0] == '1';
-    if (full_tile) k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
+    if (!full_tile && tc_persistent())
+        k_conv_tc_p<<<tc_pgrid((int)n * 4), TC_THREADS, P_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t, (int)n * 4);
+    else if (full_tile) k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
     else {
         // BSW_TC_EPI_DIRECT=1: the per-lane (uncoalesced) epilogue, for A/B runs; results are identical
         static const bool direct = getenv("BSW_TC_EPI_DIRECT") && getenv("BSW_TC_EPI_DIRECT")[0] == '1';

@@ -179,6 +179,12 @@ int bsw_bins_level_is_uniform(const bsw_bins *b, int level);
  * bsw_rows6_verify_read returns and resets {bins that differ from the exact function (must be 0), worst error of a
  * trusted bin in thousandths of its window, bins checked, bins that took the exact path}. */
 int bsw_rows6_set_verify(int on);
+/* Mapping of the affine-row table kernel: lanes of a warp that share one row (2, 4, 8 or 32; 0 = default 4, i.e. eight
+ * rows per warp).  Every setting emits the same integers; exposed for A/B timing and the parity test. */
+int bsw_rows6_set_lanes_per_row(int lpr);
+/* Launch shape of the tcgen05 convolutions: 1 = persistent kernel (one CTA per SM walking half-image tiles with a TMEM
+ * ping-pong), 0 = one CTA per tile, -1 = default (persistent; BSW_TC_PERSIST=0 overrides).  Bit-identical results. */
+int bsw_set_conv_mode(int mode);
 int bsw_rows6_verify_read(uint64_t *out4_host);
 int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
                          const float *scale_dev, int64_t scale_stream_stride, const double *endpoints_dev,

@@ -509,3 +509,32 @@ def test_affine_kernels_forced_on_non_uniform_rows_fall_back_to_the_exact_functi
     b = _run_2p(ends, mu, sc, S, q, states, sym, mode=0)
     c = _run_2p(ends, mu, sc, S, q, states, sym, mode=-1)       # classification -> generic
     assert a[0] == b[0] == c[0] and np.array_equal(a[1], b[1]) and a[2] == b[2] == c[2]
+
+
+@pytest.mark.parametrize("L,S,q", [(2048, 1024, 10), (3072, 256, 8), (93, 64, 6)])
+def test_affine_rows_mapping_does_not_change_the_integers(L, S, q):
+    """k_rows6 deals a warp to 32/LPR rows (LPR lanes per row, 32/LPR chunks per lane one after the other).  A chunk's
+    arithmetic does not depend on the mapping, so LPR = 2, 4, 8 and 32 (the one-row-per-warp kernel of the first version)
+    must leave identical streams and symbols -- including a row count that is not a multiple of the rows per warp, dead
+    tails (needle-sharp rows) and symbols in them."""
+    B = 5
+    ends, mu, sc = _level_case(L, S, q, B, seed=17)
+    sc[:, ::5] = np.float32((2. / 255.) / 8.)
+    mu[:, 1::9] *= 4
+    rs = np.random.RandomState(23)
+    sym = rs.randint(0, S, size=(B, L)).astype(np.int16)
+    sym[:, :4] = [0, S - 1, 1, S // 2]
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(7000 + b, seed=900 + b)
+        states.append([int(v) for v in w] + [head])
+    res = {}
+    try:
+        for lpr in (32, 8, 4, 2):
+            check(lib().bsw_rows6_set_lanes_per_row(lpr))
+            res[lpr] = _run_2p(ends, mu, sc, S, q, states, sym, mode=1)
+    finally:
+        check(lib().bsw_rows6_set_lanes_per_row(0))
+    ref = _run_2p(ends, mu, sc, S, q, states, sym, mode=0)
+    for lpr, got in res.items():
+        assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and got[2] == ref[2], f"lanes per row = {lpr}"

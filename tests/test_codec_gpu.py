@@ -15,6 +15,7 @@ from bitswap_b200.model import Model                 # noqa: E402
 from bitswap_b200.codec import BitSwapCodec, Bins, BITSWAP, BBANS   # noqa: E402
 from bitswap_b200.streams import StreamSet           # noqa: E402
 from bitswap_b200.rand import ImageBins              # noqa: E402
+from bitswap_b200._lib import lib, check           # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-4          # north_star: per-latent mu/sigma within 1e-4 of the reference torch model
@@ -221,6 +222,38 @@ def test_p3_tc_single_layers(label, cfg):
     worst_o, worst_s = _tc_case(cfg, 3)
     print(f"tcgen05 {label}: max |err| vs torch-f32 oracle {worst_o:.2e}, vs SIMT f32 path {worst_s:.2e}")
     assert worst_o < TOL and worst_s < TOL
+
+
+def test_p3_tc_persistent_kernel_equals_per_tile_kernels():
+    """k_conv_tc_p (one CTA per SM walking half-image tiles, TMEM ping-pong, default) against the per-tile grids
+    (k_conv_tc / k_conv_tc_h): same k-block and MMA order per accumulator, same epilogue arithmetic -> bit-identical mu and
+    sigma.  B = 80 gives 320 tiles per conv, i.e. up to three tiles per CTA: both accumulator buffers are reused and the
+    TMA ring runs across tile boundaries; every conv shape on the path (in-convs with 1 and 25 taps, dense 3x3, 5x5)."""
+    B = 80
+    cfg = CodecConfig(xs=(3, 32, 32), nz=2, zchannels=8, nprocessing=1, resdepth=1, reswidth=252)
+    sd = synthetic.synthetic_state_dict(cfg, seed=61, varied=True)
+    m = Model.from_config(cfg, max_batch=B, use_tensor_cores=True).load_state_dict(sd)
+    m.compress()
+    rs = np.random.RandomState(4)
+    gx = torch.from_numpy((rs.randint(0, 256, (B, cfg.xdim)) - 127.5) / 127.5).cuda()
+    gz = torch.from_numpy(rs.uniform(-5, 5, (B, cfg.zdim))).cuda()
+    out = {}
+    try:
+        for mode in (0, 1):
+            check(lib().bsw_set_conv_mode(mode))
+            res = []
+            for i in range(cfg.nz):
+                mu, sc = m.infer(i)(gx if i == 0 else gz)
+                res += [mu.clone(), sc.clone()]
+                mu, sc = m.generate(i)(gz)
+                res += [mu.clone(), sc.clone()]
+            torch.cuda.synchronize()
+            out[mode] = res
+    finally:
+        check(lib().bsw_set_conv_mode(-1))
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)
+    assert all(torch.isfinite(t).all() for t in out[1])
 
 
 def test_p3_tc_cifar8_full():
