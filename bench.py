@@ -422,6 +422,7 @@ def main():
                        "streams": int(counts[:, 1].sum())}
     # ---- per-kernel times: the same steps with the lanes run back to back (identical launch shapes) ---------------
     codec.serial = True
+    codec.set_dual_stream(0)
     for _ in range(1):
         codec.encode(ss, x_dev)
         codec.decode(ss, B, out=out_dev)
@@ -433,6 +434,8 @@ def main():
     torch.cuda.synchronize()
     assert torch.equal(out_dev, x_dev)
     codec.serial = False
+    if args.dual_stream > 0:
+        codec.set_dual_stream(args.dual_stream)
     barrier()
     t = torch.tensor([total_ms, enc_ms, dec_ms, gat_ms], dtype=torch.float64, device=dev)
     if world > 1:

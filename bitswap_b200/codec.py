@@ -98,7 +98,9 @@ class BitSwapCodec:
                   "push_x", "prior", "rows_z", "rows_x")
 
     def set_dual_stream(self, on=True):
-        """True: convs on a high-priority internal stream, coder kernels on a low-priority one (default off)."""
+        """True: overlap mode -- the recursion is enqueued as a dependency graph on three internal streams (nets, float64
+        table kernels, serial coder kernels), so that the tensor-pipe and the FP64-pipe work of one chain share the SMs;
+        False (default): plain program order on the caller's stream.  Same results either way."""
         check(lib().bsw_codec_set_dual_stream(self._h, int(on)))
 
     def set_two_phase(self, on=True):

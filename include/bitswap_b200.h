@@ -182,6 +182,10 @@ int bsw_rows6_set_verify(int on);
 /* Mapping of the affine-row table kernel: lanes of a warp that share one row (2, 4, 8 or 32; 0 = default 4, i.e. eight
  * rows per warp).  Every setting emits the same integers; exposed for A/B timing and the parity test. */
 int bsw_rows6_set_lanes_per_row(int lpr);
+/* Launch shape of the affine-row table kernel: ctas > 0 = persistent launch of that many CTAs walking the work items with
+ * a grid stride (leaves the block scheduler free to co-schedule other streams' kernels), 0 = one CTA per work item,
+ * -1 = default (BSW_R6_PERSIST or 0).  Same integers. */
+int bsw_rows6_set_persistent(int ctas);
 /* Launch shape of the tcgen05 convolutions: 1 = persistent kernel (one CTA per SM walking half-image tiles with a TMEM
  * ping-pong), 0 = one CTA per tile, -1 = default (persistent; BSW_TC_PERSIST=0 overrides).  Bit-identical results. */
 int bsw_set_conv_mode(int mode);

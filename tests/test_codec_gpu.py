@@ -421,6 +421,41 @@ def test_pipelined_codec_equals_single_codec():
     assert ss.export_lists() == states
 
 
+@pytest.mark.parametrize("name,tc,scheme,lanes", [("cifar8", True, BITSWAP, 2), ("tiny3", False, BBANS, 1), ("imagenetcrop4", True, BITSWAP, 1)])
+def test_overlap_mode_equals_program_order(name, tc, scheme, lanes):
+    """bsw_codec_set_dual_stream(1) enqueues the recursion as a dependency graph on three internal streams (nets / float64
+    table kernels / serial coder kernels) so that one chain's tensor-pipe and FP64-pipe work overlap.  It must leave
+    exactly the streams the plain program order leaves -- three chained images per stream, so every buffer is reused
+    across images -- and decode them back, with the overlap on in both directions."""
+    from bitswap_b200.codec import PipelinedCodec
+    B = 6
+    cfg = preset(name)
+    sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=True)
+    zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
+    pc = PipelinedCodec(cfg, sd, Bins(cfg, zend, zcen), B, lanes=lanes, use_tensor_cores=tc)
+    ss = StreamSet(B, 1 << 15)
+    imgs = synthetic.synthetic_images(cfg, 3 * B, seed=43).reshape(3, B, *cfg.xs)
+    states = []
+    for b in range(B):
+        w, head = synthetic.initial_words(5000 + b, seed=400 + b)
+        states.append([int(v) for v in w] + [head])
+    res = []
+    for mode in (0, 1):
+        pc.set_dual_stream(mode)
+        ss.import_lists(states)
+        for xi in range(3):
+            pc.encode(ss, torch.from_numpy(imgs[xi]).cuda(), scheme=scheme)
+        torch.cuda.synchronize()
+        ss.raise_on_error()
+        res.append(ss.export_lists())
+    assert res[0] == res[1]
+    for xi in (2, 1, 0):
+        out = pc.decode(ss, B, scheme=scheme)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), imgs[xi])
+    assert ss.export_lists() == states
+
+
 def test_container_variable_size_images_vs_oracle_demo_procedure():
     """BASELINE config 5 shape: variable-size images, each ONE chain over its 32x32 blocks, many images at once.
     The containers must equal what the reference's demo procedure (demo_compress.py:113-162,268-284) yields when the
