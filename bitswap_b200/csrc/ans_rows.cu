@@ -483,6 +483,7 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
 }
 
 int launch_push_pairs(bsw_streams *s, int first, int count, const void *scratch, int64_t L, int bits, cudaStream_t st) {
+    BSW_MAX_SHARED_ONCE(k_push_pairs);
     k_push_pairs<<<(count + BW - 1) / BW, BW * 32, 0, st>>>(*s, first, count, (const uint4 *)scratch, L, bits);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
@@ -539,7 +540,7 @@ int bsw_logistic_2p(int phase, bool pop, bsw_streams *s, int first, int count, c
     BSW_REQUIRE(s && first >= 0 && count > 0 && first + count <= s->B, "stream range out of bounds");
     BSW_REQUIRE(mu && sc && endp && sym && scratch && L > 0 && L < 65536 * 32, "two-phase coder: bad arguments");
     BSW_REQUIRE(ers == 0 || ers >= S, "two-phase coder: endpoint rows must hold S doubles (+1e300 padded)");
-    BSW_REQUIRE(scratch_bytes >= bsw_rows_scratch_bytes(count, L), "two-phase coder: scratch too small");
+    BSW_REQUIRE(scratch_bytes >= (pop ? bsw_rows_scratch_bytes(count, L) : (size_t)count * L * 16), "two-phase coder: scratch too small");
     BSW_REQUIRE((((uintptr_t)scratch) & 15) == 0, "two-phase coder: scratch must be 16-byte aligned");
     if (meta) {
         if (phase == 1 && !pop) return launch_push_pairs(s, first, count, scratch, L, bits, st);

@@ -460,7 +460,7 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
                      int q, void *scratch, size_t scratch_bytes, cudaStream_t st) {
     BSW_REQUIRE(S >= 8 && S <= 1024 && (S & 3) == 0, "affine coder: support must be a multiple of 4 in [8, 1024]");
     BSW_REQUIRE(bits >= 8 && bits <= 31 && q >= 0 && q < bits, "affine coder: bits/quantbits out of range");
-    BSW_REQUIRE(scratch_bytes >= bsw_rows6_scratch_bytes(count, L), "affine coder: scratch too small");
+    BSW_REQUIRE(scratch_bytes >= (pop ? bsw_rows6_scratch_bytes(count, L) : (size_t)count * L * 16), "affine coder: scratch too small");
     const R6RowMeta *mt = (const R6RowMeta *)meta;
     const int64_t mrs = ers == 0 ? 0 : 1;
     uint4 *pairs = (uint4 *)scratch;
@@ -472,10 +472,11 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
         const int env_lpr = g_lpr > 0 ? g_lpr : env_lpr0;
         if (g_verify && !g_vstat) { BSW_CUDA(cudaMalloc(&g_vstat, 32)); BSW_CUDA(cudaMemset(g_vstat, 0, 32)); }
 #define R6_LAUNCH(POP_, VER_, LPR_)                                                                                             \
+    BSW_MAX_SHARED_ONCE((k_rows6<POP_, VER_, LPR_>));                                                                             \
     k_rows6<POP_, VER_, LPR_><<<r6_grid((L + 32 / LPR_ - 1) / (32 / LPR_), (count + 15) / 16), 512, 0, st>>>(                     \
         count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, POP_ ? nullptr : sym, bits, q, POP_ ? nullptr : pairs,                 \
         POP_ ? bases : nullptr, POP_ ? fix : nullptr, VER_ ? g_vstat : nullptr, 0)
-#define R6_PICK(VER_, LPR_) do { if (pop) R6_LAUNCH(true, VER_, LPR_); else R6_LAUNCH(false, VER_, LPR_); } while (0)
+#define R6_PICK(VER_, LPR_) do { if (pop) { R6_LAUNCH(true, VER_, LPR_); } else { R6_LAUNCH(false, VER_, LPR_); } } while (0)
         if (g_verify) { if (env_lpr == 32) R6_PICK(true, 32); else R6_PICK(true, 4); }
         else if (env_lpr == 32) R6_PICK(false, 32);
         else if (env_lpr == 8) R6_PICK(false, 8);
@@ -485,6 +486,7 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
 #undef R6_LAUNCH
     } else {
         BSW_REQUIRE(pop, "affine coder: phase B of a push is k_push_pairs");
+        BSW_MAX_SHARED_ONCE(k_pop6);
         k_pop6<<<(count + PW6 - 1) / PW6, PW6 * 32, 0, st>>>(*s, first, count, mu, mss, sc, sss, endp, ers, mt, mrs, bases, fix, sym, L, S, bits, q);
     }
     BSW_LAUNCH_CHECK();

@@ -6,6 +6,7 @@
 // One call codes ONE image per stream for `count` streams.  Every step is a kernel enqueued on the
 // caller's stream; symbols, centres, mu/sigma and the ANS state stay in HBM between levels -- the
 // reference's 2*nz GPU<->CPU round trips per image (cifar_compress.py:42-43,66) do not exist here.
+#include <stdlib.h>
 #include <vector>
 #include "bsw_common.cuh"
 #include "nets.cuh"
@@ -109,8 +110,10 @@ extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int 
     c->launches = 0;
     int lo_p = 0, hi_p = 0;
     BSW_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));          // (numerically lower = higher priority)
-    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_ser, cudaStreamNonBlocking, hi_p));
-    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_conv, cudaStreamNonBlocking, hi_p < lo_p ? hi_p + 1 : hi_p));
+    // BSW_CODEC_PRIO: 2 = serial > conv > rows, 1 = serial > (conv = rows), 0 = all equal (A/B runs)
+    static const int prio = getenv("BSW_CODEC_PRIO") ? atoi(getenv("BSW_CODEC_PRIO")) : 2;
+    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_ser, cudaStreamNonBlocking, prio >= 1 ? hi_p : lo_p));
+    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_conv, cudaStreamNonBlocking, prio >= 2 && hi_p < lo_p ? hi_p + 1 : lo_p));
     BSW_CUDA(cudaStreamCreateWithPriority(&c->st_rows, cudaStreamNonBlocking, lo_p));
     for (auto &e : c->ev) BSW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = c;

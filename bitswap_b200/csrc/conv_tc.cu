@@ -842,6 +842,9 @@ int bsw_model_tc_prepare(bsw_model *m) {
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    // one SM-wide L1/shared split for every kernel of the path (see bsw_prefer_max_shared)
+    bsw_prefer_max_shared(k_conv_tc); bsw_prefer_max_shared(k_conv_tc_c2); bsw_prefer_max_shared(k_conv_tc_h<true>);
+    bsw_prefer_max_shared(k_conv_tc_h<false>); bsw_prefer_max_shared(k_conv_tc_p); bsw_prefer_max_shared(k_given_to_planes);
     m->tc_ready = true;
     return BSW_OK;
 }

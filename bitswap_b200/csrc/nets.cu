@@ -201,6 +201,7 @@ static int launch_conv_simt(const ConvArgs &a, int64_t n, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         BSW_CUDA(cudaFuncSetAttribute(k_conv_simt<KS, TCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bsw_prefer_max_shared(k_conv_simt<KS, TCO>);       // same L1/shared split as every other kernel of the path
         attr_done = true;
     }
     dim3 grid((unsigned)n, a.CoutP / COT);

@@ -54,7 +54,8 @@ int main(int argc, char **argv) {
         switch (mode) {
             case 0: case 1: muf = (float)((urand() - 0.5) * 10); scf = (float)(0.1 + 0.9 * urand()); break;
             case 2: muf = (float)((urand() - 0.5) * 14); scf = 0.1f + (float)(0.01 * urand()); break;             // sharp
-            case 3: muf = (float)((urand() < 0.5 ? -1 : 1) * (7 + 20 * urand())); scf = (float)(0.1 + 0.9 * urand()); break;  // mass outside
+            case 3: muf = (float)((urand() < 0.5 ? -1 : 1) * (7 + 20 * urand()));                                     // mass outside the grid,
+                    scf = (it % 16 == 3) ? (float)((2. / 255.) / 8.) * (float)(1 + 30 * urand()) : (float)(0.1 + 0.9 * urand()); break;  // half of them needle-sharp (|t| >> 700 at the grid)
             case 4: muf = (float)((urand() - 0.5) * 4); scf = (float)(0.5 + 3 * urand()); break;                    // very wide
             case 5: muf = (float)((urand() - 0.5) * 12); scf = (float)(0.1 + 0.9 * urand()); break;
             case 6: muf = (float)((urand() - 0.5) * 2.4); scf = (urand() < 0.3) ? (float)((2. / 255.) / 8.) : (float)(0.00098 + 0.7 * urand() * urand()); break;
