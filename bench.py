@@ -302,6 +302,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="sub-batches coded concurrently on separate CUDA streams (1 = off)")
     ap.add_argument("--lane-size", type=int, default=0, help="streams per lane (0 = batch/lanes); the last lane takes the remainder")
+    ap.add_argument("--free-running", type=int, default=1, help="1: the lanes are joined once at the end of the timed region instead of after "
+                    "every encode/decode call (keeps their phase offsets); forced off when a collective needs all lanes (N > 1)")
+    ap.add_argument("--stagger-us", type=float, default=4000.0, help="start offset between neighbouring lanes (microseconds; 0 = none)")
     ap.add_argument("--dual-stream", type=int, default=-1, help="codec stream mode (bsw_codec_set_dual_stream); -1 = library default")
     ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
     ap.add_argument("--crop-images", type=int, default=100)
@@ -343,7 +346,9 @@ def main():
     zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
     bins = Bins(cfg, zend, zcen)
     lanes = max(1, args.lanes)
-    codec = PipelinedCodec(cfg, sd, bins, B, lanes=lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size)
+    codec = PipelinedCodec(cfg, sd, bins, B, lanes=lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size,
+                           stagger_us=args.stagger_us if lanes > 1 else 0.0)
+    free_running = bool(args.free_running) and world == 1 and lanes > 1
     two_phase = not args.fused_coder
     codec.set_two_phase(two_phase)
     if args.dual_stream >= 0:
@@ -395,6 +400,11 @@ def main():
             gather_step()
         codec.decode(ss, B, out=out_dev)
     barrier()
+    # free-running lanes: every lane chains its own encode -> decode -> encode ...; ONE join before the closing event, so the
+    # timed region still contains all the work of its K steps (per-direction times are then not separable: a lane may be
+    # decoding while its neighbour encodes)
+    codec.free_running = free_running
+    codec.restagger()
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     ev[0].record()
@@ -406,8 +416,11 @@ def main():
             W, M, counts = gather_step()
         ev[3 * i + 2].record()
         codec.decode(ss, B, out=out_dev)
+        if free_running and i == args.steps - 1:
+            codec.join()
         ev[3 * i + 3].record()
     torch.cuda.synchronize()
+    codec.free_running = False
     total_ms = ev[0].elapsed_time(ev[-1])
     enc_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps))
     gat_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps))
@@ -554,7 +567,9 @@ def main():
                        "bins": "synthetic uniform grids + float32 equal-mass top level", "images": "iid uniform uint8",
                        "l2": "per-step working set (3 x 268 MB activations + streams) >> 126 MB L2: no explicit flush needed",
                        "parallelism": f"streams sharded over {world} GPU(s); within a GPU {codec.lanes} sub-batches of {Bl} on separate CUDA streams"},
-            "encode_Mpixel_s": px_job / (enc_ms * 1e-3) / 1e6, "decode_Mpixel_s": px_job / (dec_ms * 1e-3) / 1e6,
+            "encode_Mpixel_s": None if free_running else px_job / (enc_ms * 1e-3) / 1e6,
+            "decode_Mpixel_s": None if free_running else px_job / (dec_ms * 1e-3) / 1e6,
+            "lanes_free_running": free_running, "lane_stagger_us": codec.stagger_us,
             "Mdim_s": value * cfg.xs[0],
             "bits_per_dim": float(acct["net_bits_per_dim"].mean()),
             "bits": {"net_bits_per_dim": float(acct["net_bits_per_dim"].mean()),

@@ -154,7 +154,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(x) = x > 0 ? x : exp(x) - 1 (utils/torch/modules.py:229-241 F.elu).  exp by the hardware ex2 (2 ulp of the result,
+// |error| <= 2.4e-7 absolute after the subtraction): far inside the 1e-4 bar on mu/sigma (measured in the P3 tests) and
+// a third of expm1f's instructions -- the epilogue's ALU work, not its bytes, is what the convs wait for.
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 
 struct TcArgs {
     int taps, ks;
@@ -258,56 +261,62 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
         }
     } else {
         // ===== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., columns of accumulator (w-2)/4 =====
+        // Coalesced through shared memory (see k_conv_tc_h): once acc_bar has fired every pipeline stage is idle, so each
+        // warp transposes its 32 px x 32 ch chunks through a private padded tile in the stage memory and moves whole
+        // 128-byte lines (tcgen05.ld hands a lane one pixel's 32 channels: written directly that is 32 scattered 16-byte
+        // pieces per store instruction).  Same arithmetic, same order -> same bits as the direct epilogue.
         const int ew = warp - 2;
         const int half = ew >> 2;
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int p = half * 128 + quad * 32 + lane;     // pixel == GEMM row
         mbar_wait(acc_bar, 0);
         tc_fence_after();
-        const int64_t row = ((int64_t)img * 256 + p) * 256;
+        float *tile = reinterpret_cast<float *>(smem) + ew * (32 * 36);          // 32 rows x 36 floats (144 B stride)
+        const int rsub = lane >> 3, col4 = (lane & 7) * 4;
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += 32) {
             const int c0 = co0 + cc;
-            uint32_t rr[32], rc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN + cc, rr);
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + 256 + half * BN + cc, rc);
-            float v[32];
+            {
+                uint32_t rr[32], rc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN + cc, rr);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + 256 + half * BN + cc, rc);
+                float4 *trow = reinterpret_cast<float4 *>(tile + lane * 36);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (__uint_as_float(rr[i]) + __uint_as_float(rc[i])) + __ldg(a.bias + c0 + i);
-            if (a.resid) {
-                const float4 *rp = reinterpret_cast<const float4 *>(a.resid + row + c0);
+                for (int i = 0; i < 8; ++i)
+                    trow[i] = make_float4(__uint_as_float(rr[4 * i]) + __uint_as_float(rc[4 * i]),
+                                          __uint_as_float(rr[4 * i + 1]) + __uint_as_float(rc[4 * i + 1]),
+                                          __uint_as_float(rr[4 * i + 2]) + __uint_as_float(rc[4 * i + 2]),
+                                          __uint_as_float(rr[4 * i + 3]) + __uint_as_float(rc[4 * i + 3]));
+            }
+            __syncwarp();
+            const float4 bq = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + col4));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 q = rp[i];
-                    v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            for (int k = 0; k < 8; ++k) {
+                const int r = 4 * k + rsub;
+                const int64_t prow = ((int64_t)img * 256 + half * 128 + quad * 32 + r) * 256 + c0 + col4;
+                float4 x = *reinterpret_cast<const float4 *>(tile + r * 36 + col4);
+                x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;      // (main+cross)+bias
+                if (a.resid) {
+                    const float4 q = *reinterpret_cast<const float4 *>(a.resid + prow);
+                    x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+                }
+                if (a.T_elu) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+                if (a.T) *reinterpret_cast<float4 *>(a.T + prow) = x;
+                if (a.A_hi) {
+                    float y[4] = {x.x, x.y, x.z, x.w};
+                    uint32_t hi[2], lo[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        float x0 = a.A_elu ? elu1(y[2 * i]) : y[2 * i], x1 = a.A_elu ? elu1(y[2 * i + 1]) : y[2 * i + 1];
+                        __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                        __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
+                    *reinterpret_cast<uint2 *>(a.A_hi + prow) = make_uint2(hi[0], hi[1]);
+                    *reinterpret_cast<uint2 *>(a.A_lo + prow) = make_uint2(lo[0], lo[1]);
                 }
             }
-            if (a.T_elu) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = elu1(v[i]);
-            }
-            if (a.T) {
-                float4 *tp = reinterpret_cast<float4 *>(a.T + row + c0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) tp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (a.A_hi) {
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x0 = a.A_elu ? elu1(v[2 * i]) : v[2 * i], x1 = a.A_elu ? elu1(v[2 * i + 1]) : v[2 * i + 1];
-                    __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                    __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                uint4 *hp = reinterpret_cast<uint4 *>(a.A_hi + row + c0), *lp = reinterpret_cast<uint4 *>(a.A_lo + row + c0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    hp[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                    lp[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-                }
-            }
+            __syncwarp();                                 // the tile is rewritten by the next chunk
         }
         tc_fence_before();
     }
@@ -877,15 +886,17 @@ int bsw_tc_split(bsw_model *m, const float *in, int which, int64_t n, cudaStream
     return BSW_OK;
 }
 
-// Persistent kernel (k_conv_tc_p) is the default for every tensor-core conv; BSW_TC_PERSIST=0 selects the per-tile grids
-// (A/B runs, identical results).  Grid = one CTA per SM of the current device (BSW_TC_PGRID overrides), at most one per tile.
+// Which convs run on the persistent kernel k_conv_tc_p: a bit mask -- 1 = dense 3x3, 2 = dense 5x5 (and larger), 4 = in-convs.
+// Default 0 (BSW_TC_PERSIST overrides): measured on B200 at 1024 images the per-tile grids win or tie once their epilogue is
+// coalesced (the persistent kernel's half-image tiles fetch the weight tile twice, and the convs are bound by L2->SM bytes per
+// MMA and by the power cap, not by the exposed epilogue).  Results are bit-identical either way.
 static int g_tc_mode = -1;
-static bool tc_persistent() {
-    static const bool on = !(getenv("BSW_TC_PERSIST") && getenv("BSW_TC_PERSIST")[0] == '0');
-    return g_tc_mode < 0 ? on : g_tc_mode == 1;
+static bool tc_persistent(int which) {
+    static const int env = getenv("BSW_TC_PERSIST") ? atoi(getenv("BSW_TC_PERSIST")) : 0;
+    return (((g_tc_mode < 0) ? env : g_tc_mode) & which) != 0;
 }
 extern "C" int bsw_set_conv_mode(int mode) {
-    BSW_REQUIRE(mode >= -1 && mode <= 1, "bsw_set_conv_mode: -1 (default), 0 (per-tile grids) or 1 (persistent)");
+    BSW_REQUIRE(mode >= -1 && mode <= 7, "bsw_set_conv_mode: -1 (default) or a mask of 1 (dense 3x3) | 2 (dense 5x5) | 4 (in-convs)");
     g_tc_mode = mode;
     return BSW_OK;
 }
@@ -923,7 +934,7 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     // B=1024 -- the MMAs already run at the sustained bf16 rate, so hiding the epilogue buys nothing and the re-fetched
     // weight tiles cost the 5x5.  Full tile stays the default here; BSW_TC_HALFTILE=1 selects the other one.
     static const bool half_tile = getenv("BSW_TC_HALFTILE") && getenv("BSW_TC_HALFTILE")[0] == '1';
-    if (!use_cluster && !half_tile && tc_persistent())
+    if (!use_cluster && !half_tile && tc_persistent(c.ks <= 3 ? 1 : 2))
         k_conv_tc_p<<<tc_pgrid((int)n * 4), TC_THREADS, P_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
                                                                            s.map_hi, s.map_lo, t, (int)n * 4);
     else if (!use_cluster && half_tile)
@@ -956,7 +967,7 @@ int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
     static const bool full_tile = getenv("BSW_TC_FULLTILE") && getenv("BSW_TC_FULLTILE")[0] == '1';
-    if (!full_tile && tc_persistent())
+    if (!full_tile && tc_persistent(4))
         k_conv_tc_p<<<tc_pgrid((int)n * 4), TC_THREADS, P_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t, (int)n * 4);
     else if (full_tile) k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
     else {

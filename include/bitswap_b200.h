@@ -41,6 +41,9 @@ int         bsw_has_tensor_cores(void);
 /* Measures this GPU's peak float64 FMA rate (DFMA/s, lanes) with a register-resident kernel: the roofline
  * denominator of the float64 row-table kernel (the driver's MEASURED_PEAKS.json has no FP64 figure). */
 int         bsw_measure_fp64_peak(double *dfma_per_s);
+/* Enqueues a one-thread kernel that holds `stream` for about `microseconds` (<= 1 s).  Scheduling aid: the multi-lane
+ * codec offsets its lanes in time with it (bitswap_b200/codec.py PipelinedCodec). */
+int         bsw_stream_delay(double microseconds, void *stream);
 /* Device self-test: the lean cdf of the throughput kernels vs the exact (IEEE division + libdevice exp) cdf on n
  * random finite (endpoint, mu, sigma) triples, far tails included.  example_host: 5 doubles or NULL. */
 int         bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_host, double *example_host);
@@ -186,8 +189,9 @@ int bsw_rows6_set_lanes_per_row(int lpr);
  * a grid stride (leaves the block scheduler free to co-schedule other streams' kernels), 0 = one CTA per work item,
  * -1 = default (BSW_R6_PERSIST or 0).  Same integers. */
 int bsw_rows6_set_persistent(int ctas);
-/* Launch shape of the tcgen05 convolutions: 1 = persistent kernel (one CTA per SM walking half-image tiles with a TMEM
- * ping-pong), 0 = one CTA per tile, -1 = default (persistent; BSW_TC_PERSIST=0 overrides).  Bit-identical results. */
+/* Launch shape of the tcgen05 convolutions: a mask of the convs that run on the persistent kernel (one CTA per SM walking
+ * half-image tiles with a TMEM ping-pong) instead of one CTA per tile -- 1 = dense 3x3, 2 = dense 5x5, 4 = in-convs;
+ * -1 = default (BSW_TC_PERSIST or 0).  Bit-identical results. */
 int bsw_set_conv_mode(int mode);
 int bsw_rows6_verify_read(uint64_t *out4_host);
 int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
@@ -220,6 +224,22 @@ int bsw_bins_device_ptrs(bsw_bins *b, int level, const double **zend_dev, const 
 int bsw_gather_zcentres(const bsw_bins *b, int level, const int16_t *sym_dev, float *out_dev, int64_t n_streams,
                         void *stream);
 int bsw_gather_xcentres(const uint8_t *x_dev, float *out_dev, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * f3  Sampling epilogue and bin fit of discretize() (discretization.py:30-118).
+ * minmax_dev: uint32 [2 * dim] running extrema (order-preserving encoding), reset before a level.
+ * bsw_discretize_sample: out[r,d] = float16(mu[r,d] + scale[r,d] * eps), eps = log(u) - log1p(-u) with u clamped to
+ *   [bound, 1 - bound] (utils/torch/rand.py:6-20), and folds the float16 values into the extrema.  scale_row_stride 0 = one
+ *   shared scale row.  bsw_discretize_fold: fold float16 samples produced elsewhere (the top-level prior draw).
+ * bsw_discretize_edges: np.linspace(min, max, 2^q + 1) per dimension -> endpoints [dim][2^q - 1] and centres [dim][2^q]
+ *   in float64 (KBinsDiscretizer strategy='uniform', discretization.py:105-118).
+ * ---------------------------------------------------------------------------------------------- */
+int bsw_discretize_reset(uint32_t *minmax_dev, int dim, void *stream);
+int bsw_discretize_sample(const float *mu_dev, const float *scale_dev, int64_t scale_row_stride, const float *u_dev, float bound,
+                          void *out_half_dev, uint32_t *minmax_dev, int64_t rows, int dim, void *stream);
+int bsw_discretize_fold(const void *samples_half_dev, uint32_t *minmax_dev, int64_t rows, int dim, void *stream);
+int bsw_discretize_edges(const uint32_t *minmax_dev, int dim, int quantbits, double *endpoints_dev, int64_t endp_row_stride,
+                         double *centres_dev, int64_t cen_row_stride, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a8-a10  The inference-time VAE.
