@@ -466,6 +466,9 @@ int launch_rows(int phase, bool pop, bsw_streams *s, int first, int count, const
     // BSW_ROWS_EXACT=1: evaluate the exact cdf for every bin instead of screening with bsw_cdf_apx (A/B switch; same output)
     static const bool env_exact = getenv("BSW_ROWS_EXACT") && getenv("BSW_ROWS_EXACT")[0] == '1';
     const bool exact = bits > 31 || env_exact;
+    BSW_MAX_SHARED_ONCE((k_rows<NB, true, false>)); BSW_MAX_SHARED_ONCE((k_rows<NB, true, true>));
+    BSW_MAX_SHARED_ONCE((k_rows<NB, false, false>)); BSW_MAX_SHARED_ONCE((k_rows<NB, false, true>));
+    BSW_MAX_SHARED_ONCE(k_pop_coarse<NB>); BSW_MAX_SHARED_ONCE(k_push_pairs);
     if (phase == 0) {
         if (pop) {
             if (exact) k_rows<NB, true, false><<<grid, RW * 32, 0, st>>>(count, L, mu, mss, sc, sss, endp, ers, nullptr, bits, q, nullptr, coarse, fix, kp);

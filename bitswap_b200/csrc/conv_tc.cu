@@ -716,6 +716,153 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__
     }
 }
 
+// mu/sigma heads on the tensor cores: the 3x3 W -> (n_mu + n_sc <= 32) convolution that ends every net
+// (cifar_train.py:349,368,411,426), with the scale transforms and the UnSqueeze2d index map of the x head in the epilogue.
+// GEMM per image: M = 256 pixels (two UMMA M=128 halves), N = 32 (output channels zero-padded), K = taps x 256.
+// {main, cross} x 2 halves x 32 columns = 128 TMEM columns and 3 x 36 KB stages, so two CTAs share an SM and one's
+// epilogue / start-up runs under the other's MMAs.  Narrow-N MMAs are bound by the A-operand bytes (shared memory reads
+// and L2 -> SM), not by the tensor pipe: the point is to stop spending 16 ms per step in FP32 FMAs (k_conv_simt).
+constexpr int HD_N = 32;
+constexpr int HD_WTILE = HD_N * BK * 2;                       // 2 KB
+constexpr int HD_STAGE = 2 * TILE_BYTES + 2 * HD_WTILE;        // 36 KB
+constexpr int HD_NSTAGE = 3;
+constexpr int HD_SMEM_BYTES = HD_NSTAGE * HD_STAGE + 1024 + 256;
+constexpr uint32_t IDESC_HD = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HD_N >> 3) << 17) | ((128u >> 4) << 24);
+
+struct HeadArgs {
+    int taps, ks;
+    const float *bias;       // [>= n_mu + n_sc]
+    float *mu, *scale;
+    int n_mu, n_sc, scale_kind, out_mode, out_dim;
+};
+
+__device__ __forceinline__ float hd_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float hd_softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }   // modules.py:112-114
+__device__ __forceinline__ float hd_scale(float r, int kind) {      // same expressions as nets.cu scale_transform
+    switch (kind) {
+        case SCALE_INFER:   return 0.1f + 0.9f * hd_sigmoid(r + 2.f);                               // cifar_train.py:349,368
+        case SCALE_DEEPGEN: return 0.1f + 0.9f * hd_softplus(r + 0.54132485461291810f);             // :426
+        case SCALE_X:       return ((2.f / 255.f) / 8.f) + hd_softplus(r);                          // :411 / imagenetcrop :417
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_conv_tc_head(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
+               const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, HeadArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = (uint64_t *)(smem + HD_NSTAGE * HD_STAGE);
+    uint64_t *empty_bar = full_bar + HD_NSTAGE;
+    uint64_t *acc_bar = empty_bar + HD_NSTAGE;
+    uint32_t *tmem_ptr = (uint32_t *)(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img = blockIdx.x;
+    const int nkb = a.taps * 8;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_lo) : "memory");
+        for (int s = 0; s < HD_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {     // 128 columns: main [0,64) = two halves x 32, cross [64,128)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {     // ===== TMA producer =====
+            const int r = a.ks / 2;
+            int stage = 0, phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                int tap = kb >> 3, c0 = (kb & 7) * BK;
+                int dy = tap / a.ks, dx = tap - dy * a.ks;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t *st = smem + stage * HD_STAGE;
+                mbar_expect_tx(&full_bar[stage], HD_STAGE);
+                tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img);
+                tma_load_4d(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img);
+                tma_load_3d(st + 2 * TILE_BYTES, &wmap_hi, &full_bar[stage], c0, 0, tap);
+                tma_load_3d(st + 2 * TILE_BYTES + HD_WTILE, &wmap_lo, &full_bar[stage], c0, 0, tap);
+                if (++stage == HD_NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {     // ===== MMA issuer =====
+            int stage = 0, phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                uint32_t sbase = smem_u32(smem + stage * HD_STAGE);
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t aoff = half * (128 * BK * 2) + kk * 32;
+                        uint64_t a_hi = make_desc_sw64(sbase + aoff);
+                        uint64_t a_lo = make_desc_sw64(sbase + TILE_BYTES + aoff);
+                        uint64_t b_hi = make_desc_sw64(sbase + 2 * TILE_BYTES + kk * 32);
+                        uint64_t b_lo = make_desc_sw64(sbase + 2 * TILE_BYTES + HD_WTILE + kk * 32);
+                        uint32_t d_main = tmem_base + half * HD_N, d_cross = tmem_base + 64 + half * HD_N;
+                        const uint32_t acc = (kb | kk) != 0;
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(d_main), "l"(a_hi), "l"(b_hi), "r"(IDESC_HD), "r"(acc) : "memory");
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(d_cross), "l"(a_lo), "l"(b_hi), "r"(IDESC_HD), "r"(acc) : "memory");
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(d_cross), "l"(a_hi), "l"(b_lo), "r"(IDESC_HD), "r"(1u) : "memory");
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == HD_NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_bar);
+        }
+    } else {
+        // ===== epilogue: warp -> (pixel half, TMEM lane quadrant); a lane owns one pixel and all 32 output channels.
+        // For a fixed channel the 32 lanes write 32 consecutive pixels of the flat CHW mu / sigma rows: whole lines. =====
+        const int ew = warp - 2;
+        const int half = ew >> 2;
+        const int quad = warp & 3;
+        const int p = half * 128 + quad * 32 + lane;
+        const int y = p >> 4, x = p & 15;
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        uint32_t rr[32], rc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * HD_N, rr);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + 64 + half * HD_N, rc);
+        float *mu_row = a.mu + (int64_t)img * a.out_dim;
+        float *sc_row = a.scale ? a.scale + (int64_t)img * a.out_dim : nullptr;
+#pragma unroll
+        for (int c = 0; c < HD_N; ++c) {
+            if (c >= a.n_mu + a.n_sc) break;
+            const bool is_mu = c < a.n_mu;
+            const int o = is_mu ? c : c - a.n_mu;
+            float r = (__uint_as_float(rr[c]) + __uint_as_float(rc[c])) + __ldg(a.bias + c);
+            if (!is_mu) r = hd_scale(r, a.scale_kind);
+            float *dst = is_mu ? mu_row : sc_row;
+            if (a.out_mode == OUT_HEAD_Z) dst[o * 256 + p] = r;
+            else dst[(o >> 2) * 1024 + (2 * y + ((o >> 1) & 1)) * 32 + 2 * x + (o & 1)] = r;      // UnSqueeze2d, modules.py:205-207
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // float32 NHWC -> bf16 hi/lo planes (used once per net, after the SIMT in-conv)
 __global__ void k_split_planes(const float *__restrict__ in, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -809,24 +956,26 @@ int bsw_model_tc_prepare(bsw_model *m) {
     }
     // weights: [tap][o=256][c=Kc] bf16 hi/lo planes, K (=c) innermost; Kc = 256 for the dense convs, 32 for the in-convs
     std::vector<TcSlot> *slots = new std::vector<TcSlot>();
-    std::vector<char> is_in(m->convs.size(), 0);
-    for (auto &np : m->infer) is_in[np.in_conv] = 1;
-    for (auto &np : m->gen) is_in[np.in_conv] = 1;
+    std::vector<char> is_in(m->convs.size(), 0), is_head(m->convs.size(), 0);
+    for (auto &np : m->infer) { is_in[np.in_conv] = 1; is_head[np.head] = 1; }
+    for (auto &np : m->gen) { is_in[np.in_conv] = 1; is_head[np.head] = 1; }
     for (size_t ci_ = 0; ci_ < m->convs.size(); ++ci_) {
         ConvSlot &c = m->convs[ci_];
         bool dense = (c.Cin == m->d.reswidth && c.Cout == m->d.reswidth);
         bool inconv = is_in[ci_] && c.Cin <= 32 && c.Cout == m->d.reswidth;
-        if (!dense && !inconv) continue;
+        bool head = is_head[ci_] && !dense && c.Cin == m->d.reswidth && c.Cout <= HD_N;
+        if (!dense && !inconv && !head) continue;
         BSW_REQUIRE(!c.host_w.empty(), "tc_prepare: host weights already released");
         const int taps = c.ks * c.ks;
-        const int Kc = dense ? 256 : 32;
-        std::vector<__nv_bfloat16> hi((size_t)taps * 256 * Kc), lo(hi.size());
+        const int Kc = inconv ? 32 : 256;
+        const int rows = head ? HD_N : 256;              // output-channel rows per tap (heads: zero padded to 32)
+        std::vector<__nv_bfloat16> hi((size_t)taps * rows * Kc), lo(hi.size());
         for (int tp = 0; tp < taps; ++tp)
             for (int ci = 0; ci < Kc; ++ci)
-                for (int o = 0; o < 256; ++o) {
-                    float w = ci < c.CinP ? c.host_w[((size_t)tp * c.CinP + ci) * c.CoutP + o] : 0.f;
+                for (int o = 0; o < rows; ++o) {
+                    float w = (ci < c.CinP && o < c.CoutP) ? c.host_w[((size_t)tp * c.CinP + ci) * c.CoutP + o] : 0.f;
                     __nv_bfloat16 h = __float2bfloat16_rn(w);
-                    size_t idx = ((size_t)tp * 256 + o) * Kc + ci;
+                    size_t idx = ((size_t)tp * rows + o) * Kc + ci;
                     hi[idx] = h;
                     lo[idx] = __float2bfloat16_rn(w - __bfloat162float(h));
                 }
@@ -837,9 +986,9 @@ int bsw_model_tc_prepare(bsw_model *m) {
         ts->wbufs.push_back(c.w_hi);
         ts->wbufs.push_back(c.w_lo);
         TcSlot s;
-        cuuint64_t dims[3] = {(cuuint64_t)Kc, 256, (cuuint64_t)taps};
-        cuuint64_t str[2] = {(cuuint64_t)Kc * 2, (cuuint64_t)256 * Kc * 2};
-        cuuint32_t box[3] = {BK, BN, 1};
+        cuuint64_t dims[3] = {(cuuint64_t)Kc, (cuuint64_t)rows, (cuuint64_t)taps};
+        cuuint64_t str[2] = {(cuuint64_t)Kc * 2, (cuuint64_t)rows * Kc * 2};
+        cuuint32_t box[3] = {BK, (cuuint32_t)(head ? HD_N : BN), 1};
         if (int rc = encode_map(&s.map_hi, c.w_hi, 3, dims, str, box)) return rc;
         if (int rc = encode_map(&s.map_lo, c.w_lo, 3, dims, str, box)) return rc;
         c.tc_index = (int)slots->size();
@@ -851,6 +1000,8 @@ int bsw_model_tc_prepare(bsw_model *m) {
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_head, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM_BYTES));
+    bsw_prefer_max_shared(k_conv_tc_head);
     // one SM-wide L1/shared split for every kernel of the path (see bsw_prefer_max_shared)
     bsw_prefer_max_shared(k_conv_tc); bsw_prefer_max_shared(k_conv_tc_c2); bsw_prefer_max_shared(k_conv_tc_h<true>);
     bsw_prefer_max_shared(k_conv_tc_h<false>); bsw_prefer_max_shared(k_conv_tc_p); bsw_prefer_max_shared(k_given_to_planes);
@@ -946,6 +1097,24 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     else
         k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
                                                                            s.map_hi, s.map_lo, t);
+    BSW_LAUNCH_CHECK();
+    return BSW_OK;
+}
+
+// Heads: reads the planes the last ResNet conv wrote (in_planes), writes mu / sigma.  BSW_TC_HEADS=0 keeps the float32 SIMT
+// kernel (A/B runs).
+bool bsw_conv_tc_head_available(bsw_model *m, const ConvSlot &c) {
+    static const bool off = getenv("BSW_TC_HEADS") && getenv("BSW_TC_HEADS")[0] == '0';
+    return !off && m->tc_ready && c.tc_index >= 0 && c.Cout <= HD_N && c.Cin == m->d.reswidth;
+}
+int bsw_conv_tc_head(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st) {
+    TcState *ts = (TcState *)m->tc_state;
+    BSW_REQUIRE(ts && c.tc_index >= 0 && a.n_mu + a.n_sc <= HD_N, "bsw_conv_tc_head: conv has no tensor-core head weights");
+    const TcSlot &s = (*(std::vector<TcSlot> *)m->tc_slots)[c.tc_index];
+    HeadArgs h;
+    h.taps = c.ks * c.ks; h.ks = c.ks; h.bias = c.bias; h.mu = a.mu; h.scale = a.scale; h.n_mu = a.n_mu; h.n_sc = a.n_sc;
+    h.scale_kind = a.scale_kind; h.out_mode = a.out_mode; h.out_dim = a.out_dim;
+    k_conv_tc_head<<<(unsigned)n, TC_THREADS, HD_SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1], s.map_hi, s.map_lo, h);
     BSW_LAUNCH_CHECK();
     return BSW_OK;
 }

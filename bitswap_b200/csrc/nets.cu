@@ -437,6 +437,8 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
     const int Wp = m->Wp;
     const bool has_blocks = !np.blocks.empty();
     const bool use_tc = m->d.use_tensor_cores && m->tc_ready;
+    // heads on the tensor cores: they read the trunk as bf16 planes, which the last ResNet conv then has to write
+    const bool tc_head = use_tc && has_blocks && bsw_conv_tc_head_available(m, m->convs[np.head]);
     float *T = m->bufT, *A = m->bufA, *B = m->bufB;
     {   // in-conv
         const ConvSlot &c = m->convs[np.in_conv];
@@ -476,6 +478,7 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
                     a.in = B; a.resid = T; a.T = T; a.T_elu = last_layer ? 1 : 0;
                     a.A = (last_layer && last_block) ? nullptr : A; a.A_elu = 1;
                     a.in_planes = 1; a.A_planes = (last_layer && last_block) ? -1 : 0;
+                    if (last_layer && last_block && tc_head) { a.A_planes = 0; a.A_elu = 0; }     // planes = the trunk itself (already ELU'd)
                 }
                 int rc;
                 prof->begin(c.ks == 5 ? CAT_CONV_DENSE5 : CAT_CONV_DENSE3, st);
@@ -495,7 +498,9 @@ static int run_net(bsw_model *m, const NetPlan &np, const float *given, int64_t 
         a.out_mode = np.out_mode; a.mu = mu; a.scale = scale; a.n_mu = np.n_mu; a.n_sc = np.n_sc;
         a.scale_kind = np.scale_kind; a.out_dim = np.out_dim;
         prof->begin(CAT_CONV_HEAD, st);
-        if (int rc = bsw_conv_simt(a, c.ks, n, st)) return rc;
+        a.in_planes = 0;
+        if (tc_head) { if (int rc = bsw_conv_tc_head(m, c, a, n, st)) return rc; }
+        else if (int rc = bsw_conv_simt(a, c.ks, n, st)) return rc;
         prof->end(st);
         ++*launches;
     }

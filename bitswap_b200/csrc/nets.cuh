@@ -104,5 +104,7 @@ int bsw_model_run(bsw_model *m, bool infer, int level, const float *given, int64
 int bsw_model_tc_prepare(bsw_model *m);
 void bsw_model_tc_release(bsw_model *m);
 int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st);
+bool bsw_conv_tc_head_available(bsw_model *m, const ConvSlot &c);
+int bsw_conv_tc_head(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st);
 int bsw_tc_split(bsw_model *m, const float *in, int which, int64_t n, cudaStream_t st);
 int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, cudaStream_t st, int *launches);
