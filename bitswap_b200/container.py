@@ -120,7 +120,9 @@ def decompress_images(codec, containers, channels=3, scheme=BITSWAP, hwc_quirk=F
     dev = torch.zeros((max(nblk), n, channels, 32, 32), dtype=torch.uint8, device=torch.device("cuda", codec.device))
     for t in reversed(range(max(nblk))):
         active = sum(1 for b in nblk if b > t)
-        dev[t, :active] = codec.decode(ss, active, first=0, scheme=scheme)
+        codec.decode(ss, active, first=0, scheme=scheme, out=dev[t, :active])
+    if hasattr(codec, "join"):                                             # (free-running multi-lane codec: lanes -> current stream)
+        codec.join()
     host = dev.cpu().numpy()                                               # one transfer for every block of every image
     blocks = [_model_to_blocks(host[:nblk[j], j], hwc_quirk) for j in range(n)]
     ss.raise_on_error()

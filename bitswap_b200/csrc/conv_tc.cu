@@ -268,10 +268,24 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
         const int ew = warp - 2;
         const int half = ew >> 2;
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
         float *tile = reinterpret_cast<float *>(smem) + ew * (32 * 36);          // 32 rows x 36 floats (144 B stride)
         const int rsub = lane >> 3, col4 = (lane & 7) * 4;
+        const int64_t pbase = ((int64_t)img * 256 + half * 128 + quad * 32 + rsub) * 256 + co0 + col4;   // + (4 k) * 256 + cc
+        // The residual is the trunk itself (updated in place: resid == T), so the compiler may not move its loads above the
+        // stores of an earlier row -- left alone, every row's HBM latency is paid in series (ncu: the conv2 launches ran
+        // 0.98 ms against 0.75 ms for conv1, long_scoreboard on the residual loads).  The loads are therefore issued
+        // explicitly one 32-channel chunk ahead: chunk 0's before the accumulator is even ready (they do not depend on
+        // it), chunk c+1's before chunk c's arithmetic and stores.  A thread re-reads nothing it has written (chunks are
+        // disjoint channel ranges of its own rows), so the in-place update stays exact.
+        float4 q[8], qn[8];
+        auto load_resid = [&](float4 (&dst)[8], int cc) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                dst[k] = a.resid ? *reinterpret_cast<const float4 *>(a.resid + pbase + (int64_t)(4 * k) * 256 + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        load_resid(q, 0);
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += 32) {
             const int c0 = co0 + cc;
@@ -288,17 +302,15 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
                                           __uint_as_float(rr[4 * i + 3]) + __uint_as_float(rc[4 * i + 3]));
             }
             __syncwarp();
+            if (cc + 32 < BN) load_resid(qn, cc + 32);
             const float4 bq = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + col4));
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int r = 4 * k + rsub;
-                const int64_t prow = ((int64_t)img * 256 + half * 128 + quad * 32 + r) * 256 + c0 + col4;
+                const int64_t prow = pbase + (int64_t)(4 * k) * 256 + cc;
                 float4 x = *reinterpret_cast<const float4 *>(tile + r * 36 + col4);
                 x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;      // (main+cross)+bias
-                if (a.resid) {
-                    const float4 q = *reinterpret_cast<const float4 *>(a.resid + prow);
-                    x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
-                }
+                if (a.resid) { x.x += q[k].x; x.y += q[k].y; x.z += q[k].z; x.w += q[k].w; }
                 if (a.T_elu) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
                 if (a.T) *reinterpret_cast<float4 *>(a.T + prow) = x;
                 if (a.A_hi) {
@@ -316,6 +328,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
                     *reinterpret_cast<uint2 *>(a.A_lo + prow) = make_uint2(lo[0], lo[1]);
                 }
             }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = qn[k];
             __syncwarp();                                 // the tile is rewritten by the next chunk
         }
         tc_fence_before();
@@ -328,9 +342,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
     }
 }
 
-// min-blocks 2 only caps the register count (<= 96/thread, 30.7K per CTA) so that one coder CTA (k_rows, 32.8K
-// registers) can share the SM with a conv CTA; shared memory still limits the kernel itself to one CTA per SM.
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// One CTA per SM (shared memory); ~150 registers per thread for the epilogue's two residual chunks in flight.  That leaves
+// 17 K registers per SM: room for the serial coder CTAs of another lane (11 K), not for a 32 K-register table CTA -- by
+// measurement nothing is lost: the convs run at the board's power cap, so FP64 work beside them only lowers the clock
+// (DESIGN.md 5.3).
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
           const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
     conv_tc_body<false>(amap_hi, amap_lo, wmap_hi, wmap_lo, a);

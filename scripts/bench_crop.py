@@ -71,7 +71,7 @@ def run_crop(args, rank, world, local):
     from bitswap_b200 import synthetic, parallel
     from bitswap_b200.config import preset
     from bitswap_b200.model import Model
-    from bitswap_b200.codec import BitSwapCodec, Bins
+    from bitswap_b200.codec import PipelinedCodec, Bins
     from bitswap_b200.container import compress_images, decompress_images
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
@@ -89,9 +89,10 @@ def run_crop(args, rank, world, local):
     mine = shards[rank]
     sd = synthetic.synthetic_state_dict(cfg, seed=50, varied=False)
     zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
-    model = Model.from_config(cfg, max_batch=max(1, len(mine)), use_tensor_cores=True).load_state_dict(sd)
-    model.compress()
-    codec = BitSwapCodec(cfg, model, Bins(cfg, zend, zcen), max(1, len(mine)))
+    # a chain is sequential in its blocks, so one step of one lane is a string of small latency-bound kernels (<= 100 images:
+    # less than one wave of conv CTAs); the lanes of a free-running PipelinedCodec code disjoint groups of chains concurrently
+    lanes = max(1, min(args.lanes if args.lanes > 0 else 4, len(mine)))
+    codec = PipelinedCodec(cfg, sd, Bins(cfg, zend, zcen), max(1, len(mine)), lanes=lanes, use_tensor_cores=True, free_running=True)
     my_images = [images[i] for i in mine]
 
     def sync():
@@ -149,7 +150,7 @@ def run_crop(args, rank, world, local):
                                        f"image ONE chain over its blocks, imagenetcrop model (nz=4, W=256, conditional x-scale), chains dealt to "
                                        f"{world} GPU(s) by block count; step = compress every chain + gather the containers on rank 0 + decompress",
                            "chains_per_gpu": [len(s) for s in shards], "blocks_per_gpu": [sum(costs[i] for i in s) for s in shards],
-                           "serial_depth_blocks": max(costs), "layout": "HWC quirk of imagenetcrop_compress.py:130" if args.hwc_quirk else "CHW (demo_compress.py:120)",
+                           "serial_depth_blocks": max(costs), "lanes_per_gpu": lanes, "layout": "HWC quirk of imagenetcrop_compress.py:130" if args.hwc_quirk else "CHW (demo_compress.py:120)",
                            "note": "latency-bound by construction: a chain is sequential in its blocks; timed through the public API with host "
                                    "images in and host containers/images out (this IS the end-to-end number)"},
                 "encode_Mpixel_s": px * args.steps / enc / 1e6, "decode_Mpixel_s": px * args.steps / dec / 1e6,

@@ -492,6 +492,13 @@ def test_container_variable_size_images_vs_oracle_demo_procedure():
     for img, rec in zip(images, back):
         h, w = img.shape[0] - img.shape[0] % 32, img.shape[1] - img.shape[1] % 32
         assert np.array_equal(rec, img[:h, :w])
+    # the same through a free-running multi-lane codec (what `bench.py --config crop` runs): identical containers
+    from bitswap_b200.codec import PipelinedCodec
+    pc = PipelinedCodec(cfg, sd, Bins(cfg, zend, zcen), len(images), lanes=3, use_tensor_cores=False, free_running=True)
+    conts_pc = compress_images(pc, images, excess_state_len=3000)
+    assert all(np.array_equal(a, b) for a, b in zip(conts, conts_pc))
+    back_pc = decompress_images(pc, conts_pc)
+    assert all(np.array_equal(a, b) for a, b in zip(back, back_pc))
 
 
 def test_gpu_discretize_builds_usable_bins():
