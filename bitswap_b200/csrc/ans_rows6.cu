@@ -88,7 +88,11 @@ template <bool POP, bool VERIFY, int LPR>
 __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, const float *__restrict__ mu, int64_t mss,
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const R6RowMeta *__restrict__ meta, int64_t mrs, const int16_t *__restrict__ sym, int bits, int q,
-        uint4 *__restrict__ pairs, uint32_t *__restrict__ bases, uint2 *__restrict__ fix, unsigned long long *vstat, int zero) {
+        uint4 *__restrict__ pairs, uint32_t *__restrict__ bases, uint2 *__restrict__ fix, unsigned long long *vstat, int zero,
+        double mult2) {
+    // mult2 = (2^bits - 2^q) * 2^20 (:28; the pmf in 2^-20 fixed point: < 2^51) comes in as an argument: FP64 instructions
+    // read it straight from the constant bank, where a value derived in the kernel was re-derived (2 moves + a DMUL) by
+    // the compiler in every 4-bin group to save two registers.
     constexpr int RPW = 32 / LPR;                         // rows per warp
     constexpr int CPL = 32 / LPR;                         // chunks per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,7 +108,6 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
     if (si >= count) continue;
     const bool valid = rg * RPW + lane / LPR < L;
     const int64_t row = valid ? rg * RPW + lane / LPR : L - 1;   // (lanes past the end redo the last row, write nothing)
-    const double mult2 = (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0;   // :28; pmf in 2^-20 fixed point: < 2^51
     R6Plan pl;
     {
         const R6RowMeta M = meta[row * mrs];
@@ -475,7 +478,8 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
     BSW_MAX_SHARED_ONCE((k_rows6<POP_, VER_, LPR_>));                                                                             \
     k_rows6<POP_, VER_, LPR_><<<r6_grid((L + 32 / LPR_ - 1) / (32 / LPR_), (count + 15) / 16), 512, 0, st>>>(                     \
         count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, POP_ ? nullptr : sym, bits, q, POP_ ? nullptr : pairs,                 \
-        POP_ ? bases : nullptr, POP_ ? fix : nullptr, VER_ ? g_vstat : nullptr, 0)
+        POP_ ? bases : nullptr, POP_ ? fix : nullptr, VER_ ? g_vstat : nullptr, 0,                                                \
+        (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0)
 #define R6_PICK(VER_, LPR_) do { if (pop) { R6_LAUNCH(true, VER_, LPR_); } else { R6_LAUNCH(false, VER_, LPR_); } } while (0)
         if (g_verify) { if (env_lpr == 32) R6_PICK(true, 32); else R6_PICK(true, 4); }
         else if (env_lpr == 32) R6_PICK(false, 32);
