@@ -115,7 +115,6 @@ def _set_argtypes(L):
         "bsw_bins_level_is_uniform": [P, I],
         "bsw_rows6_set_verify": [I],
         "bsw_rows6_set_lanes_per_row": [I],
-        "bsw_rows6_set_persistent": [I],
         "bsw_set_conv_mode": [I],
         "bsw_rows6_verify_read": [P],
         "bsw_logistic_push_2p": [P, I, I, P, L64, P, L64, P, L64, P, L64, I, I, I, P, L64, P],
@@ -157,7 +156,7 @@ def _set_argtypes(L):
 EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure_fp64_peak", "bsw_selftest_cdf", "bsw_selftest_cdf_apx", "bsw_streams_create", "bsw_streams_destroy", "bsw_streams_count",
            "bsw_streams_capacity", "bsw_streams_import", "bsw_streams_fill", "bsw_streams_sizes", "bsw_streams_min_words", "bsw_streams_rest_words", "bsw_streams_export",
            "bsw_streams_device_ptrs", "bsw_streams_pack", "bsw_streams_unpack", "bsw_streams_pack_trimmed", "bsw_streams_unpack_trimmed", "bsw_streams_total_words", "bsw_ans_tables", "bsw_ans_push", "bsw_ans_pop",
-           "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_logistic_scratch_bytes", "bsw_set_rows_mode", "bsw_bins_level_is_uniform", "bsw_rows6_set_verify", "bsw_rows6_verify_read", "bsw_rows6_set_lanes_per_row", "bsw_rows6_set_persistent", "bsw_set_conv_mode", "bsw_logistic_push_2p",
+           "bsw_logistic_pmfs", "bsw_logistic_tables", "bsw_logistic_push", "bsw_logistic_pop", "bsw_logistic_scratch_bytes", "bsw_set_rows_mode", "bsw_bins_level_is_uniform", "bsw_rows6_set_verify", "bsw_rows6_verify_read", "bsw_rows6_set_lanes_per_row", "bsw_set_conv_mode", "bsw_logistic_push_2p",
            "bsw_logistic_pop_2p", "bsw_bins_create",
            "bsw_bins_destroy", "bsw_bins_device_ptrs", "bsw_gather_zcentres", "bsw_gather_xcentres",
            "bsw_model_create", "bsw_model_destroy", "bsw_model_load_conv", "bsw_model_load_gen_std",

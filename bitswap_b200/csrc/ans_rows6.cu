@@ -97,17 +97,11 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
     constexpr int CPL = 32 / LPR;                         // chunks per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = lane % LPR;                             // my position among the lanes of my row
-    // Work items = (group of RPW rows) x (group of 16 streams), walked with a grid stride: the (row groups, stream groups)
-    // grid has one item per CTA; a small 1-D grid is a persistent launch (every CTA resident from the start, so the block
-    // scheduler never holds another stream's kernel behind a queue of undispatched table CTAs).
-    const int64_t nrg = (L + RPW - 1) / RPW;
-    const int64_t nitems = nrg * ((count + 15) / 16);
-    for (int64_t item = (int64_t)blockIdx.y * gridDim.x + blockIdx.x; item < nitems; item += (int64_t)gridDim.x * gridDim.y) {
-    const int64_t rg = item % nrg;
-    const int si = (int)(item / nrg) * 16 + warp;
-    if (si >= count) continue;
-    const bool valid = rg * RPW + lane / LPR < L;
-    const int64_t row = valid ? rg * RPW + lane / LPR : L - 1;   // (lanes past the end redo the last row, write nothing)
+    // grid = (groups of RPW rows, groups of 16 streams)
+    const int si = blockIdx.y * 16 + warp;
+    if (si >= count) return;
+    const bool valid = (int64_t)blockIdx.x * RPW + lane / LPR < L;
+    const int64_t row = valid ? (int64_t)blockIdx.x * RPW + lane / LPR : L - 1;   // (lanes past the end redo the last row, write nothing)
     R6Plan pl;
     {
         const R6RowMeta M = meta[row * mrs];
@@ -285,7 +279,6 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
             else pairs[out] = make_uint4(pf, cb + (bi < sy ? rem : 0u), (uint32_t)Mg, (uint32_t)(Mg >> 32));
         }
     }
-    }   // work items
 }
 
 // ---- phase B: pop -----------------------------------------------------------------------------------------------------------
@@ -421,13 +414,6 @@ __global__ void __launch_bounds__(PW6 * 32) k_pop6(bsw_streams sv, int first, in
     ws.close(sv, b, lane);
 }
 
-int g_r6_persist = -1;                                   // CTAs of a persistent k_rows6 launch (0: one CTA per item, -1: BSW_R6_PERSIST or 0)
-dim3 r6_grid(int64_t row_groups, int stream_groups) {
-    static const int env = getenv("BSW_R6_PERSIST") ? atoi(getenv("BSW_R6_PERSIST")) : 0;
-    const int p = g_r6_persist >= 0 ? g_r6_persist : env;
-    if (p > 0 && row_groups * stream_groups > p) return dim3((unsigned)p, 1, 1);
-    return dim3((unsigned)row_groups, (unsigned)stream_groups, 1);
-}
 unsigned long long *g_vstat = nullptr;                   // device [4], allocated on first use of the VERIFY build
 int g_verify = 0;
 int g_lpr = 0;                                           // lanes per row of k_rows6 (0: BSW_R6_LPR or the default 4)
@@ -476,7 +462,7 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
         if (g_verify && !g_vstat) { BSW_CUDA(cudaMalloc(&g_vstat, 32)); BSW_CUDA(cudaMemset(g_vstat, 0, 32)); }
 #define R6_LAUNCH(POP_, VER_, LPR_)                                                                                             \
     BSW_MAX_SHARED_ONCE((k_rows6<POP_, VER_, LPR_>));                                                                             \
-    k_rows6<POP_, VER_, LPR_><<<r6_grid((L + 32 / LPR_ - 1) / (32 / LPR_), (count + 15) / 16), 512, 0, st>>>(                     \
+    k_rows6<POP_, VER_, LPR_><<<dim3((unsigned)((L + 32 / LPR_ - 1) / (32 / LPR_)), (count + 15) / 16), 512, 0, st>>>(            \
         count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, POP_ ? nullptr : sym, bits, q, POP_ ? nullptr : pairs,                 \
         POP_ ? bases : nullptr, POP_ ? fix : nullptr, VER_ ? g_vstat : nullptr, 0,                                                \
         (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0)
@@ -502,11 +488,6 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
 extern "C" int bsw_rows6_set_lanes_per_row(int lpr) {
     BSW_REQUIRE(lpr == 0 || lpr == 2 || lpr == 4 || lpr == 8 || lpr == 32, "bsw_rows6_set_lanes_per_row: 0 (default), 2, 4, 8 or 32");
     g_lpr = lpr;
-    return BSW_OK;
-}
-extern "C" int bsw_rows6_set_persistent(int ctas) {
-    BSW_REQUIRE(ctas >= -1 && ctas <= 65535, "bsw_rows6_set_persistent: -1 (default), 0 (one CTA per work item) or the CTA count of a persistent launch");
-    g_r6_persist = ctas;
     return BSW_OK;
 }
 extern "C" int bsw_rows6_set_verify(int on) { g_verify = on ? 1 : 0; return BSW_OK; }

@@ -31,8 +31,8 @@ struct bsw_codec {
     int64_t launches;
     BswProf prof;
     // overlap mode (bsw_codec_set_dual_stream(c, 1)): the recursion is enqueued as a DAG on three internal streams --
-    // st_conv (nets), st_rows (parallel float64 table kernels, lowest priority), st_ser (serial integer coder kernels,
-    // highest priority: few small CTAs on the critical path) -- see the comment above bsw_codec_encode.
+    // st_conv (nets), st_rows (parallel float64 table kernels), st_ser (serial integer coder kernels) -- see the comment
+    // above bsw_codec_encode.
     cudaStream_t st_conv = nullptr, st_rows = nullptr, st_ser = nullptr;
     cudaEvent_t ev[16];
     int ev_next = 0;
@@ -110,10 +110,12 @@ extern "C" int bsw_codec_create(bsw_codec **out, bsw_model *m, bsw_bins *b, int 
     c->launches = 0;
     int lo_p = 0, hi_p = 0;
     BSW_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));          // (numerically lower = higher priority)
-    // BSW_CODEC_PRIO: 2 = serial > conv > rows, 1 = serial > (conv = rows), 0 = all equal (A/B runs)
-    static const int prio = getenv("BSW_CODEC_PRIO") ? atoi(getenv("BSW_CODEC_PRIO")) : 2;
-    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_ser, cudaStreamNonBlocking, prio >= 1 ? hi_p : lo_p));
-    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_conv, cudaStreamNonBlocking, prio >= 2 && hi_p < lo_p ? hi_p + 1 : lo_p));
+    // equal priorities: on this part a running higher-priority kernel keeps lower-priority CTAs from being dispatched at
+    // all (measured: convs on a high-priority stream and table kernels on a low-priority one took the SUM of their solo
+    // times), so priorities can only serialise
+    (void)hi_p;
+    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_ser, cudaStreamNonBlocking, lo_p));
+    BSW_CUDA(cudaStreamCreateWithPriority(&c->st_conv, cudaStreamNonBlocking, lo_p));
     BSW_CUDA(cudaStreamCreateWithPriority(&c->st_rows, cudaStreamNonBlocking, lo_p));
     for (auto &e : c->ev) BSW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = c;

@@ -99,14 +99,6 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3, uint16_t mask) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -137,10 +129,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -170,11 +158,6 @@ struct TcArgs {
     int A_elu;
 };
 
-// CLUSTER: the two N-half CTAs of an image form a 2-CTA cluster and share the activation tile: CTA 0 loads the hi
-// plane, CTA 1 the lo plane, each TMA multicast into both CTAs' shared memory (L2->SM traffic per CTA 48 -> 32 KB
-// per k-block).  A stage is free only when BOTH consumers released it, so the MMA commit arrives on both CTAs'
-// empty barriers.
-template <bool CLUSTER>
 __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const CUtensorMap &amap_lo, const CUtensorMap &wmap_hi,
                                              const CUtensorMap &wmap_lo, const TcArgs &a) {
     extern __shared__ uint8_t smem_raw[];
@@ -193,7 +176,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
         asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_lo) : "memory");
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER ? 2 : 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -202,10 +185,9 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    if (CLUSTER) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const int crank = CLUSTER ? (int)blockIdx.y : 0;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -218,13 +200,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t *st = smem + stage * STAGE_BYTES;
                 mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                if (CLUSTER) {
-                    if (crank == 0) tma_load_4d_mc(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img, 3);
-                    else tma_load_4d_mc(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img, 3);
-                } else {
-                    tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img);
-                    tma_load_4d(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img);
-                }
+                tma_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r, img);
+                tma_load_4d(st + TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r, img);
                 tma_load_3d(st + 2 * TILE_BYTES, &wmap_hi, &full_bar[stage], c0, co0, tap);
                 tma_load_3d(st + 2 * TILE_BYTES + WTILE_BYTES, &wmap_lo, &full_bar[stage], c0, co0, tap);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -253,8 +230,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
                         umma_bf16(d_cross, a_hi, b_lo, 1);
                     }
                 }
-                if (CLUSTER) umma_commit_mc(&empty_bar[stage], 3);   // frees the stage in BOTH CTAs when these MMAs retire
-                else umma_commit(&empty_bar[stage]);
+                umma_commit(&empty_bar[stage]);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             umma_commit(acc_bar);                        // accumulators complete
@@ -334,7 +310,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
         }
         tc_fence_before();
     }
-    if (CLUSTER) cluster_sync_all(); else __syncthreads();     // (cluster: the peer may still signal my barriers until here)
+    __syncthreads();
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -349,14 +325,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap &amap_hi, const C
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
           const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
-    conv_tc_body<false>(amap_hi, amap_lo, wmap_hi, wmap_lo, a);
+    conv_tc_body(amap_hi, amap_lo, wmap_hi, wmap_lo, a);
 }
-__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(TC_THREADS, 1)
-k_conv_tc_c2(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
-             const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
-    conv_tc_body<true>(amap_hi, amap_lo, wmap_hi, wmap_lo, a);
-}
-
 // Half-image variant: the default for the in-convs (0.555 -> 0.416 ms per launch at B=1024), optional for the dense convs.
 // k_conv_tc above owns the SM (192 KB of stages, all 512 TMEM columns), so the tensor
 // pipe idles while its eight epilogue warps drain the accumulators to HBM -- about half of a 3x3 launch and nearly all
@@ -365,7 +335,6 @@ k_conv_tc_c2(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant_
 // resident per SM and one's epilogue runs under the other's MMAs.  Price: the weight tile is fetched per half image
 // (L2->SM bytes per k-block and MMA row 48 KB/256 rows -> 32 KB/128 rows); the order of the k-blocks and of the MMAs
 // into each accumulator is unchanged, so results are bit-identical to the full-tile kernel.
-template <bool COAL>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_conv_tc_h(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
             const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a) {
@@ -443,108 +412,60 @@ k_conv_tc_h(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__
         const int ew = warp - 2;
         const int chalf = ew >> 2;
         const int quad = warp & 3;
-        const int p = mh * 128 + quad * 32 + lane;       // pixel
         mbar_wait(acc_bar, 0);
         tc_fence_after();
-        const int64_t row = ((int64_t)img * 256 + p) * 256;
-        if (COAL) {
-            // Coalesced epilogue.  tcgen05.ld hands every lane one pixel's 32 consecutive channels; written straight to
-            // HBM that is 32 scattered 16-byte pieces per store instruction (the LSU, not HBM, bounds the direct epilogue:
-            // ncu shows lg_throttle on every STG).  Instead the warp transposes each 32 px x 32 ch chunk through a private
-            // padded tile in the (now idle) pipeline stages, so that 8 consecutive lanes hold 128 contiguous bytes of one
-            // pixel row: residual loads, trunk stores and plane stores become 4 full lines per instruction.
-            float *tile = reinterpret_cast<float *>(smem) + ew * (32 * 36);          // 32 rows x 36 floats (144 B stride)
-            const int rsub = lane >> 3, col4 = (lane & 7) * 4;
-#pragma unroll 1
-            for (int cc = chalf * 64; cc < chalf * 64 + 64; cc += 32) {
-                const int c0 = co0 + cc;
-                {
-                    uint32_t rr[32], rc[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc, rr);
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + BN + cc, rc);
-                    float4 *trow = reinterpret_cast<float4 *>(tile + lane * 36);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        trow[i] = make_float4(__uint_as_float(rr[4 * i]) + __uint_as_float(rc[4 * i]),
-                                              __uint_as_float(rr[4 * i + 1]) + __uint_as_float(rc[4 * i + 1]),
-                                              __uint_as_float(rr[4 * i + 2]) + __uint_as_float(rc[4 * i + 2]),
-                                              __uint_as_float(rr[4 * i + 3]) + __uint_as_float(rc[4 * i + 3]));
-                }
-                __syncwarp();
-                const float4 bq = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + col4));
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int r = 4 * k + rsub;
-                    const int64_t prow = ((int64_t)img * 256 + mh * 128 + quad * 32 + r) * 256 + c0 + col4;
-                    float4 x = *reinterpret_cast<const float4 *>(tile + r * 36 + col4);
-                    x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;      // same order as the direct path: (main+cross)+bias
-                    if (a.resid) {
-                        const float4 q = *reinterpret_cast<const float4 *>(a.resid + prow);
-                        x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
-                    }
-                    if (a.T_elu) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
-                    if (a.T) *reinterpret_cast<float4 *>(a.T + prow) = x;
-                    if (a.A_hi) {
-                        float y[4] = {x.x, x.y, x.z, x.w};
-                        uint32_t hi[2], lo[2];
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            float x0 = a.A_elu ? elu1(y[2 * i]) : y[2 * i], x1 = a.A_elu ? elu1(y[2 * i + 1]) : y[2 * i + 1];
-                            __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                            __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
-                        *reinterpret_cast<uint2 *>(a.A_hi + prow) = make_uint2(hi[0], hi[1]);
-                        *reinterpret_cast<uint2 *>(a.A_lo + prow) = make_uint2(lo[0], lo[1]);
-                    }
-                }
-                __syncwarp();                             // the tile is rewritten by the next chunk
-            }
-        } else
+        // Coalesced epilogue.  tcgen05.ld hands every lane one pixel's 32 consecutive channels; written straight to
+        // HBM that is 32 scattered 16-byte pieces per store instruction (the LSU, not HBM, bounds the direct epilogue:
+        // ncu shows lg_throttle on every STG).  Instead the warp transposes each 32 px x 32 ch chunk through a private
+        // padded tile in the (now idle) pipeline stages, so that 8 consecutive lanes hold 128 contiguous bytes of one
+        // pixel row: residual loads, trunk stores and plane stores become 4 full lines per instruction.
+        float *tile = reinterpret_cast<float *>(smem) + ew * (32 * 36);          // 32 rows x 36 floats (144 B stride)
+        const int rsub = lane >> 3, col4 = (lane & 7) * 4;
 #pragma unroll 1
         for (int cc = chalf * 64; cc < chalf * 64 + 64; cc += 32) {
             const int c0 = co0 + cc;
-            uint32_t rr[32], rc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc, rr);
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + BN + cc, rc);
-            float v[32];
+            {
+                uint32_t rr[32], rc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc, rr);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + BN + cc, rc);
+                float4 *trow = reinterpret_cast<float4 *>(tile + lane * 36);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (__uint_as_float(rr[i]) + __uint_as_float(rc[i])) + __ldg(a.bias + c0 + i);
-            if (a.resid) {
-                const float4 *rp = reinterpret_cast<const float4 *>(a.resid + row + c0);
+                for (int i = 0; i < 8; ++i)
+                    trow[i] = make_float4(__uint_as_float(rr[4 * i]) + __uint_as_float(rc[4 * i]),
+                                          __uint_as_float(rr[4 * i + 1]) + __uint_as_float(rc[4 * i + 1]),
+                                          __uint_as_float(rr[4 * i + 2]) + __uint_as_float(rc[4 * i + 2]),
+                                          __uint_as_float(rr[4 * i + 3]) + __uint_as_float(rc[4 * i + 3]));
+            }
+            __syncwarp();
+            const float4 bq = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + col4));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 q = rp[i];
-                    v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            for (int k = 0; k < 8; ++k) {
+                const int r = 4 * k + rsub;
+                const int64_t prow = ((int64_t)img * 256 + mh * 128 + quad * 32 + r) * 256 + c0 + col4;
+                float4 x = *reinterpret_cast<const float4 *>(tile + r * 36 + col4);
+                x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;      // same order as the direct path: (main+cross)+bias
+                if (a.resid) {
+                    const float4 q = *reinterpret_cast<const float4 *>(a.resid + prow);
+                    x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+                }
+                if (a.T_elu) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+                if (a.T) *reinterpret_cast<float4 *>(a.T + prow) = x;
+                if (a.A_hi) {
+                    float y[4] = {x.x, x.y, x.z, x.w};
+                    uint32_t hi[2], lo[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        float x0 = a.A_elu ? elu1(y[2 * i]) : y[2 * i], x1 = a.A_elu ? elu1(y[2 * i + 1]) : y[2 * i + 1];
+                        __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                        __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
+                    *reinterpret_cast<uint2 *>(a.A_hi + prow) = make_uint2(hi[0], hi[1]);
+                    *reinterpret_cast<uint2 *>(a.A_lo + prow) = make_uint2(lo[0], lo[1]);
                 }
             }
-            if (a.T_elu) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = elu1(v[i]);
-            }
-            if (a.T) {
-                float4 *tp = reinterpret_cast<float4 *>(a.T + row + c0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) tp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (a.A_hi) {
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x0 = a.A_elu ? elu1(v[2 * i]) : v[2 * i], x1 = a.A_elu ? elu1(v[2 * i + 1]) : v[2 * i + 1];
-                    __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                    __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                uint4 *hp = reinterpret_cast<uint4 *>(a.A_hi + row + c0), *lp = reinterpret_cast<uint4 *>(a.A_lo + row + c0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    hp[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                    lp[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-                }
-            }
+            __syncwarp();                             // the tile is rewritten by the next chunk
         }
         tc_fence_before();
     }
@@ -1012,15 +933,13 @@ int bsw_model_tc_prepare(bsw_model *m) {
     }
     m->tc_slots = slots;
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
-    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_head, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM_BYTES));
     bsw_prefer_max_shared(k_conv_tc_head);
     // one SM-wide L1/shared split for every kernel of the path (see bsw_prefer_max_shared)
-    bsw_prefer_max_shared(k_conv_tc); bsw_prefer_max_shared(k_conv_tc_c2); bsw_prefer_max_shared(k_conv_tc_h<true>);
-    bsw_prefer_max_shared(k_conv_tc_h<false>); bsw_prefer_max_shared(k_conv_tc_p); bsw_prefer_max_shared(k_given_to_planes);
+    bsw_prefer_max_shared(k_conv_tc); bsw_prefer_max_shared(k_conv_tc_h);
+    bsw_prefer_max_shared(k_conv_tc_p); bsw_prefer_max_shared(k_given_to_planes);
     m->tc_ready = true;
     return BSW_OK;
 }
@@ -1067,7 +986,7 @@ extern "C" int bsw_set_conv_mode(int mode) {
     g_tc_mode = mode;
     return BSW_OK;
 }
-static unsigned tc_pgrid(int ntiles) {
+static unsigned tc_pgrid(int ntiles) {             // one CTA per SM of the current device, at most one per tile
     static int sms[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1075,8 +994,7 @@ static unsigned tc_pgrid(int ntiles) {
     if (!sms[dev]) {
         int v = 0;
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        static const int env = getenv("BSW_TC_PGRID") ? atoi(getenv("BSW_TC_PGRID")) : 0;
-        sms[dev] = env > 0 ? env : (v > 0 ? v : 148);
+        sms[dev] = v > 0 ? v : 148;
     }
     return (unsigned)(ntiles < sms[dev] ? ntiles : sms[dev]);
 }
@@ -1093,23 +1011,14 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
-    // The cluster variant is functionally identical and measured no faster on B200 (0.897 vs 0.880 ms per 3x3 launch at
-    // B=1024): the kernel issues 1.03-1.32 PFLOP/s of MMAs, i.e. it sits at the measured sustained bf16 rate, not at the
-    // L2->SM limit the multicast relieves.  It stays selectable (BSW_TC_CLUSTER=1) as the documented experiment.
-    static const bool use_cluster = getenv("BSW_TC_CLUSTER") && getenv("BSW_TC_CLUSTER")[0] == '1';
-    // Dense convs: the half-image kernel measured 0.856 (3x3) / 2.058 ms (5x5) against 0.875 / 1.896 ms for the full tile at
-    // B=1024 -- the MMAs already run at the sustained bf16 rate, so hiding the epilogue buys nothing and the re-fetched
-    // weight tiles cost the 5x5.  Full tile stays the default here; BSW_TC_HALFTILE=1 selects the other one.
-    static const bool half_tile = getenv("BSW_TC_HALFTILE") && getenv("BSW_TC_HALFTILE")[0] == '1';
-    if (!use_cluster && !half_tile && tc_persistent(c.ks <= 3 ? 1 : 2))
+    // Kernel choice by measurement (B200, 1024 images): the full tile (256 px x 128 ch per CTA) moves 4 KB of operands per
+    // 128x128x16 MMA from L2, the half-image tiles of k_conv_tc_h / k_conv_tc_p 5.3 KB -- and the convs are bound by exactly
+    // that (about 42 B/clk/SM of L2 -> SM delivery: 0.84 vs 0.87 ms for the 3x3, 1.95 vs 2.31 ms for the 5x5), so hiding the
+    // epilogue behind a TMEM ping-pong does not pay for the second weight fetch.  A 2-CTA cluster with multicast activation
+    // tiles (r1) measured no gain either (0.897 vs 0.880 ms) and is gone.  k_conv_tc_p stays selectable (bsw_set_conv_mode).
+    if (tc_persistent(c.ks <= 3 ? 1 : 2))
         k_conv_tc_p<<<tc_pgrid((int)n * 4), TC_THREADS, P_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
                                                                            s.map_hi, s.map_lo, t, (int)n * 4);
-    else if (!use_cluster && half_tile)
-        k_conv_tc_h<true><<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
-                                                                                   s.map_hi, s.map_lo, t);
-    else if (use_cluster)
-        k_conv_tc_c2<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
-                                                                              s.map_hi, s.map_lo, t);
     else
         k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->act_map[a.in_planes][0], ts->act_map[a.in_planes][1],
                                                                            s.map_hi, s.map_lo, t);
@@ -1151,16 +1060,12 @@ int bsw_conv_tc_in(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n
     t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
-    static const bool full_tile = getenv("BSW_TC_FULLTILE") && getenv("BSW_TC_FULLTILE")[0] == '1';
-    if (!full_tile && tc_persistent(4))
+    // in-convs: nine or twenty-five tiny k-blocks, all epilogue -> half-image tiles, two CTAs per SM (0.26 ms per launch at
+    // 1024 images against 0.55 ms on the full tile)
+    if (tc_persistent(4))
         k_conv_tc_p<<<tc_pgrid((int)n * 4), TC_THREADS, P_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t, (int)n * 4);
-    else if (full_tile) k_conv_tc<<<dim3((unsigned)n, 256 / BN), TC_THREADS, SMEM_BYTES, st>>>(ts->inp_map[0], ts->inp_map[1], s.map_hi, s.map_lo, t);
-    else {
-        // BSW_TC_EPI_DIRECT=1: the per-lane (uncoalesced) epilogue, for A/B runs; results are identical
-        static const bool direct = getenv("BSW_TC_EPI_DIRECT") && getenv("BSW_TC_EPI_DIRECT")[0] == '1';
-        if (direct) k_conv_tc_h<false><<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t);
-        else k_conv_tc_h<true><<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t);
-    }
+    else
+        k_conv_tc_h<<<dim3((unsigned)n, 256 / BN, 2), TC_THREADS, H_SMEM_BYTES, st>>>(ts->inp_map_h[0], ts->inp_map_h[1], s.map_hi, s.map_lo, t);
     BSW_LAUNCH_CHECK();
     *launches += 2;
     return BSW_OK;

@@ -185,10 +185,6 @@ int bsw_rows6_set_verify(int on);
 /* Mapping of the affine-row table kernel: lanes of a warp that share one row (2, 4, 8 or 32; 0 = default 4, i.e. eight
  * rows per warp).  Every setting emits the same integers; exposed for A/B timing and the parity test. */
 int bsw_rows6_set_lanes_per_row(int lpr);
-/* Launch shape of the affine-row table kernel: ctas > 0 = persistent launch of that many CTAs walking the work items with
- * a grid stride (leaves the block scheduler free to co-schedule other streams' kernels), 0 = one CTA per work item,
- * -1 = default (BSW_R6_PERSIST or 0).  Same integers. */
-int bsw_rows6_set_persistent(int ctas);
 /* Launch shape of the tcgen05 convolutions: a mask of the convs that run on the persistent kernel (one CTA per SM walking
  * half-image tiles with a TMEM ping-pong) instead of one CTA per tile -- 1 = dense 3x3, 2 = dense 5x5, 4 = in-convs;
  * -1 = default (BSW_TC_PERSIST or 0).  Bit-identical results. */
