@@ -304,7 +304,6 @@ def main():
     ap.add_argument("--lane-size", type=int, default=0, help="streams per lane (0 = batch/lanes); the last lane takes the remainder")
     ap.add_argument("--free-running", type=int, default=1, help="1: the lanes are joined once at the end of the timed region instead of after "
                     "every encode/decode call (keeps their phase offsets); forced off when a collective needs all lanes (N > 1)")
-    ap.add_argument("--stagger-us", type=float, default=4000.0, help="start offset between neighbouring lanes (microseconds; 0 = none)")
     ap.add_argument("--dual-stream", type=int, default=-1, help="codec stream mode (bsw_codec_set_dual_stream); -1 = library default")
     ap.add_argument("--fused-coder", action="store_true", help="one-warp-per-stream fused coder kernels instead of the two-phase coder")
     ap.add_argument("--crop-images", type=int, default=100)
@@ -346,8 +345,7 @@ def main():
     zend, zcen = synthetic.synthetic_bins(cfg, seed=0)
     bins = Bins(cfg, zend, zcen)
     lanes = max(1, args.lanes)
-    codec = PipelinedCodec(cfg, sd, bins, B, lanes=lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size,
-                           stagger_us=args.stagger_us if lanes > 1 else 0.0)
+    codec = PipelinedCodec(cfg, sd, bins, B, lanes=lanes, use_tensor_cores=bool(use_tc), lane_size=args.lane_size)
     free_running = bool(args.free_running) and world == 1 and lanes > 1
     two_phase = not args.fused_coder
     codec.set_two_phase(two_phase)
@@ -404,7 +402,6 @@ def main():
     # timed region still contains all the work of its K steps (per-direction times are then not separable: a lane may be
     # decoding while its neighbour encodes)
     codec.free_running = free_running
-    codec.restagger()
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     ev[0].record()
@@ -569,7 +566,7 @@ def main():
                        "parallelism": f"streams sharded over {world} GPU(s); within a GPU {codec.lanes} sub-batches of {Bl} on separate CUDA streams"},
             "encode_Mpixel_s": None if free_running else px_job / (enc_ms * 1e-3) / 1e6,
             "decode_Mpixel_s": None if free_running else px_job / (dec_ms * 1e-3) / 1e6,
-            "lanes_free_running": free_running, "lane_stagger_us": codec.stagger_us,
+            "lanes_free_running": free_running,
             "Mdim_s": value * cfg.xs[0],
             "bits_per_dim": float(acct["net_bits_per_dim"].mean()),
             "bits": {"net_bits_per_dim": float(acct["net_bits_per_dim"].mean()),

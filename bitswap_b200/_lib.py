@@ -139,7 +139,6 @@ def _set_argtypes(L):
         "bsw_codec_profile": [P, I, P, P],
         "bsw_codec_set_two_phase": [P, I],
         "bsw_codec_set_dual_stream": [P, I],
-        "bsw_stream_delay": [ctypes.c_double, P],
         "bsw_discretize_reset": [P, I, P],
         "bsw_discretize_sample": [P, P, L64, P, ctypes.c_float, P, P, L64, I, P],
         "bsw_discretize_fold": [P, P, L64, I, P],
@@ -162,7 +161,7 @@ EXPORTS = ["bsw_last_error", "bsw_version", "bsw_has_tensor_cores", "bsw_measure
            "bsw_model_create", "bsw_model_destroy", "bsw_model_load_conv", "bsw_model_load_gen_std",
            "bsw_model_finalize", "bsw_vae_infer", "bsw_vae_generate", "bsw_codec_create", "bsw_codec_destroy",
            "bsw_codec_encode", "bsw_codec_decode", "bsw_codec_last_launches", "bsw_codec_profile", "bsw_codec_set_two_phase", "bsw_codec_set_dual_stream",
-           "bsw_stream_delay", "bsw_discretize_reset", "bsw_discretize_sample", "bsw_discretize_fold", "bsw_discretize_edges"]
+           "bsw_discretize_reset", "bsw_discretize_sample", "bsw_discretize_fold", "bsw_discretize_edges"]
 
 
 def device_index(device=None):

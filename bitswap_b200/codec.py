@@ -126,7 +126,7 @@ class PipelinedCodec:
     batch-invariant.  Each lane owns a model replica (activations are per-lane anyway)."""
 
     def __init__(self, cfg: CodecConfig, state_dict, bins: Bins, max_batch: int, lanes: int = 4, use_tensor_cores=True, lane_size: int = 0,
-                 free_running: bool = False, stagger_us: float = 0.0):
+                 free_running: bool = False):
         self.cfg, self.bins, self.max_batch = cfg, bins, int(max_batch)
         self.device = bins.device
         self.lanes = max(1, min(int(lanes), self.max_batch))
@@ -137,13 +137,11 @@ class PipelinedCodec:
         self.models, self.codecs, self.streams = [], [], []
         self.serial = False          # True: run the lanes back to back on the current stream (clean per-kernel timing)
         # free_running: calls fork the lanes from the current stream but do NOT join them back -- consecutive encode()/
-        # decode() calls then chain per lane, lanes keep whatever phase offset they have, and the caller orders later work
-        # after the codec with join().  stagger_us: one-off start offset between neighbouring lanes (a delay kernel at the
-        # head of lane i's first call: i * stagger_us).  All lanes run the same program at the same speed, so without an
-        # offset their latency-bound serial coder phases coincide and nothing hides them.
+        # decode() calls then chain per lane (a lane may be decoding while its neighbour still encodes), and the caller orders
+        # later work after the codec with join().  (A start offset between the lanes was tried -- all lanes run the same
+        # program, so their latency-bound serial coder phases could coincide -- and measured no effect: they drift apart on
+        # their own within a step.)
         self.free_running = bool(free_running)
-        self.stagger_us = float(stagger_us)
-        self._staggered = False
         for _ in range(self.lanes):
             m = Model.from_config(cfg, max_batch=self.per, use_tensor_cores=use_tensor_cores, device=self.device).load_state_dict(state_dict)
             m.compress()
@@ -170,10 +168,7 @@ class PipelinedCodec:
             st = self.streams[i]
             st.wait_event(ev)
             with torch.cuda.stream(st):
-                if self.stagger_us > 0 and not self._staggered and i > 0:
-                    check(lib().bsw_stream_delay(i * self.stagger_us, cuda_stream_ptr()))
                 fn(self.codecs[i], b, n)
-        self._staggered = True
         if not self.free_running:
             self.join()
 
@@ -182,10 +177,6 @@ class PipelinedCodec:
         cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             cur.wait_stream(st)
-
-    def restagger(self):
-        """Apply the start offsets again at the next call (after a join that let the lanes catch up with each other)."""
-        self._staggered = False
 
     def encode(self, streams: StreamSet, x: torch.Tensor, first=0, scheme=BITSWAP):
         assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.shape[0] <= self.max_batch

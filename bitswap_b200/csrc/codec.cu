@@ -143,23 +143,6 @@ extern "C" int bsw_codec_set_dual_stream(bsw_codec *c, int on) {
     return BSW_OK;
 }
 
-// Holds `stream` for about `microseconds` (one thread sleeping on %globaltimer): PipelinedCodec staggers its lanes with it
-// so that the lanes' latency-bound serial coder phases do not coincide.
-__global__ void k_delay(unsigned long long ns) {
-    unsigned long long t0, t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-        __nanosleep(2000);
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    } while (t - t0 < ns);
-}
-extern "C" int bsw_stream_delay(double microseconds, void *stream) {
-    BSW_REQUIRE(microseconds >= 0 && microseconds <= 1e6, "bsw_stream_delay: 0 .. 1e6 microseconds");
-    k_delay<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)(microseconds * 1e3));
-    BSW_LAUNCH_CHECK();
-    return BSW_OK;
-}
-
 extern "C" int bsw_codec_set_two_phase(bsw_codec *c, int on) {
     BSW_REQUIRE(c, "null codec");
     c->two_phase = on ? 1 : 0;

@@ -41,9 +41,6 @@ int         bsw_has_tensor_cores(void);
 /* Measures this GPU's peak float64 FMA rate (DFMA/s, lanes) with a register-resident kernel: the roofline
  * denominator of the float64 row-table kernel (the driver's MEASURED_PEAKS.json has no FP64 figure). */
 int         bsw_measure_fp64_peak(double *dfma_per_s);
-/* Enqueues a one-thread kernel that holds `stream` for about `microseconds` (<= 1 s).  Scheduling aid: the multi-lane
- * codec offsets its lanes in time with it (bitswap_b200/codec.py PipelinedCodec). */
-int         bsw_stream_delay(double microseconds, void *stream);
 /* Device self-test: the lean cdf of the throughput kernels vs the exact (IEEE division + libdevice exp) cdf on n
  * random finite (endpoint, mu, sigma) triples, far tails included.  example_host: 5 doubles or NULL. */
 int         bsw_selftest_cdf(int64_t n, uint64_t seed, int64_t *mismatches_host, double *example_host);

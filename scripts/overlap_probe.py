@@ -98,7 +98,7 @@ def main():
     nconv, nrows = iters, iters * 8                          # roughly equal device time (measured below)
     conv_loop(2, s_conv); rows_loop(4, s_rows); torch.cuda.synchronize()
     ss.fill(w, head)
-    out = {"streams": B, "r6_warps": os.environ.get("BSW_R6_WARPS", "16")}
+    out = {"streams": B}
     out["A_conv_alone_ms"], out["A_smi"] = timed(lambda: conv_loop(nconv, s_conv))
     out["B_rows_alone_ms"], out["B_smi"] = timed(lambda: rows_loop(nrows, s_rows))
     ss.fill(w, head)
