@@ -64,15 +64,19 @@ def full(path, out):
                     f.write(f"| {k} | {r[hdr.index(k)]} | {units[hdr.index(k)]} |\n")
 
 
-CATS = [("rows_z", r"k_rows6?<", 2048), ("rows_x", r"k_rows6?<", 3072), ("pop_z", r"k_pop6|k_pop_coarse", None),
-        ("push_z", r"k_push_pairs", None), ("conv_dense3x3", r"k_conv_tc\b|k_conv_tc\(", None)]
+# category, kernel-name regex, grid_dim_x of the launch (k_rows6: rows / 8 -> 256 for a 2048-row z level, 384 for the 3072-row x level)
+CATS = [("rows_z", r"k_rows6<", 256), ("rows_x", r"k_rows6<", 384), ("pop_z", r"k_pop6", None),
+        ("push_z", r"k_push_pairs", None), ("conv_dense3x3", r"k_conv_tc\(", "ms<1.3"), ("conv_dense5x5", r"k_conv_tc\(", "ms>=1.3"),
+        ("conv_head", r"k_conv_tc_head", None), ("conv_in", r"k_conv_tc_h", None)]
 
 
 def facts(streams, out, paths):
     import json
+    import os
     import re
     acc = {}
     for path in paths:
+        label = "ncu --set full --clock-control none, " + os.path.basename(path) + " (summary: profiles/r2_ncu_final.md)"
         txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr = rows[0]
@@ -83,8 +87,14 @@ def facts(streams, out, paths):
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
             gx = int(col(r, "launch__grid_dim_x"))
+            ms_ = col(r, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(
+                units[hdr.index("gpu__time_duration.sum")].replace("second", "s").replace("msecond", "ms").replace("usecond", "us").replace("nsecond", "ns"), 1.0)
             for cat, rx, want_gx in CATS:
-                if not re.search(rx, name) or (want_gx is not None and gx != want_gx):
+                if not re.search(rx, name):
+                    continue
+                if isinstance(want_gx, int) and gx != want_gx:
+                    continue
+                if isinstance(want_gx, str) and not eval(want_gx, {"ms": ms_ * 1024.0 / float(streams)}):   # (the dense 3x3 / 5x5 convs share a kernel)
                     continue
                 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
                 rd = col(r, "dram__bytes_read.sum") * scale.get(units[hdr.index("dram__bytes_read.sum")], 1.0)
@@ -99,7 +109,7 @@ def facts(streams, out, paths):
                 a["n"] += 1; a["dram"] += rd + wr; a["f64"] += f64
                 a["ms"] += col(r, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")].replace("second", "s").replace("msecond", "ms").replace("usecond", "us").replace("nsecond", "ns"), 1.0)
                 a["inst"] += col(r, "smsp__inst_executed.sum")
-                a["src"].add(path)
+                a["src"].add(label)
                 break
     res = {}
     for cat, a in acc.items():
