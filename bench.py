@@ -19,7 +19,7 @@ state, so steps repeat without re-initialisation.
                concurrently); traffic / FP64 instruction counts from the tracked ncu summary.
   cpu_baseline the oracle port of the reference path (torch-CPU nets + float64 tables + Python-loop
                ANS) on this box's host cores: latency mode with the 5-way time split and
-               throughput mode (one single-threaded process per core), bounded samples.
+               throughput mode (cores/16 processes of 16 threads, one chain each), bounded samples.
 
 `--impl reference` times that CPU path as its own arm (the reference is pure Python and cannot be
 pip-installed/travel).  `--config crop` is BASELINE configs[4]: 100 variable-size images as
@@ -178,31 +178,34 @@ def cpu_chain(config, nimg, threads, seed=7, timers=False):
 
 
 def _tp_worker(args):
-    """Throughput-mode worker: one single-threaded process = one chain of one image, encode + decode."""
-    config, seed = args
-    e, d, _, _ = cpu_chain(config, 1, 1, seed=seed)
+    """Throughput-mode worker: one process with `threads` torch threads = one chain of one image, encode + decode."""
+    config, seed, threads = args
+    e, d, _, _ = cpu_chain(config, 1, threads, seed=seed)
     return e + d
 
 
-def _tp_init(config):
-    os.environ["OMP_NUM_THREADS"] = "1"
-    torch.set_num_threads(1)
-    _W[(config, 1)] = _cpu_setup(config, 1)
-    cpu_chain(config, 1, 1)                                   # warm-up inside the worker (first-call costs)
+def _tp_init(config, threads):
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    torch.set_num_threads(threads)
+    _W[(config, threads)] = _cpu_setup(config, threads)
+    cpu_chain(config, 1, threads)                             # warm-up inside the worker (first-call costs)
 
 
 class ThroughputPool:
-    """One single-threaded worker process per host core (the reference's throughput mode)."""
+    """All host cores on the reference's CPU path (throughput mode): `procs` worker processes of `threads`
+    torch threads each, procs x threads = cores, every worker its own chain.  16 threads per chain is where the path's torch
+    ops stop scaling; one single-threaded process per core was measured too (profiles/bench_r2_reference_arm_1thread.json:
+    0.0026 Mpixel/s on 128 cores, 45 s per image -- a 25-step arm would take 20 minutes)."""
 
-    def __init__(self, config, procs):
+    def __init__(self, config, procs, threads):
         import multiprocessing as mp
-        self.config, self.procs = config, procs
-        self.pool = mp.get_context("spawn").Pool(procs, initializer=_tp_init, initargs=(config,))
+        self.config, self.procs, self.threads = config, procs, threads
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_tp_init, initargs=(config, threads))
 
     def step(self, step_index=0):
         """Every worker codes one image (encode + decode); returns (wall seconds, images)."""
         t0 = time.perf_counter()
-        self.pool.map(_tp_worker, [(self.config, 1000 + step_index * self.procs + i) for i in range(self.procs)], chunksize=1)
+        self.pool.map(_tp_worker, [(self.config, 1000 + step_index * self.procs + i, self.threads) for i in range(self.procs)], chunksize=1)
         return time.perf_counter() - t0, self.procs
 
     def close(self):
@@ -210,24 +213,29 @@ class ThroughputPool:
         self.pool.join()
 
 
-def host_procs():
-    n = os.cpu_count() or 1
+def host_procs(threads=16):
+    """(worker processes, threads per worker) covering the host cores (bounded by free memory: ~2 GB per worker)."""
+    cores = os.cpu_count() or 1
+    threads = max(1, min(threads, cores))
+    n = max(1, cores // threads)
     try:
         import psutil
-        n = min(n, max(1, int(psutil.virtual_memory().available // (1 << 30))))     # ~1 GB per worker (torch + model + tables)
+        n = min(n, max(1, int(psutil.virtual_memory().available // (2 << 30))))
     except Exception:
         pass
-    return max(1, min(n, 128))
+    return n, threads
 
 
 def run_reference_arm(args, cfg, rank, world):
-    """The reference's own CPU implementation of the path, with all the host threads it can use: one single-threaded
-    process per core, each coding its own chain (the reference is strictly batch 1).  A step = every worker encodes and
-    decodes one image."""
+    """The reference's own CPU implementation of the path, with all the host threads it can use: `procs` processes of
+    16 threads, each coding its own chain (the reference is strictly batch 1).  A step = every worker encodes and decodes one
+    image (about 1.5 s of wall time, so a 25-step arm ends within a minute)."""
     if rank != 0:
         return
-    procs = args.ref_procs or host_procs()
-    pool = ThroughputPool(args.config, procs)
+    procs, threads = host_procs()
+    if args.ref_procs:
+        procs = args.ref_procs
+    pool = ThroughputPool(args.config, procs, threads)
     for i in range(args.warmup):
         pool.step(10000 + i)
     wall, imgs = 0.0, 0
@@ -235,11 +243,10 @@ def run_reference_arm(args, cfg, rank, world):
         w, n = pool.step(i)
         wall += w; imgs += n
     pool.close()
-    lat_threads = min(os.cpu_count() or 1, 16)
-    e, d, bpd, split = cpu_chain(args.config, 2, lat_threads, timers=True)
+    e, d, bpd, split = cpu_chain(args.config, 2, threads, timers=True)
     val = imgs * 1024 / wall / 1e6
-    sample = (f"throughput mode: {procs} single-threaded worker processes (of {os.cpu_count()} host cores), each step every worker "
-              f"encodes + decodes one image of its own chain (the reference is strictly batch 1)")
+    sample = (f"throughput mode: {procs} worker processes x {threads} torch threads (of {os.cpu_count()} host cores), each step every "
+              f"worker encodes + decodes one image of its own chain (the reference is strictly batch 1)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 tables / f32 nets / int64 coder", "data": "synthetic",
@@ -247,32 +254,33 @@ def run_reference_arm(args, cfg, rank, world):
                        "what_runs": "oracle port of the reference path (torch-CPU nets, torch float64 logistic tables, "
                                     "Python-loop ANS with Python ints) -- the reference itself is pure Python and cannot travel"},
             "bits_per_dim": bpd,
-            "latency_mode": {"threads": lat_threads, "encode_s_per_image": e / 2, "decode_s_per_image": d / 2,
-                             "Mpixel_s": 2 * 1024 / (e + d) / 1e6, "time_split": split},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "latency_mode": {"threads": threads, "encode_s_per_image": e / 2, "decode_s_per_image": d / 2,
+                             "Mpixel_s": 2 * 1024 / (e + d) / 1e6, "time_split": split,
+                             "sample": "one 2-image chain alone on the box"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs * threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def cpu_baseline_block(config, images, tp_steps):
-    """cpu_baseline of the GPU arm's line: latency mode (one chain, up to 16 threads, 5-way split) + throughput mode."""
-    lat_threads = min(os.cpu_count() or 1, 16)
-    cpu_chain(config, 1, lat_threads)
-    e, d, bpd, split = cpu_chain(config, images, lat_threads, timers=True)
+    """cpu_baseline of the GPU arm's line: latency mode (one chain alone on the box, 16 threads, 5-way split) + throughput
+    mode (all cores: processes x 16 threads, one chain each)."""
+    procs, threads = host_procs()
+    cpu_chain(config, 1, threads)
+    e, d, bpd, split = cpu_chain(config, images, threads, timers=True)
     out = {"unit": UNIT, "kind": "port",
-           "latency_mode": {"threads": lat_threads, "Mpixel_s": images * 1024 / (e + d) / 1e6, "encode_s_per_image": e / images,
+           "latency_mode": {"threads": threads, "Mpixel_s": images * 1024 / (e + d) / 1e6, "encode_s_per_image": e / images,
                             "decode_s_per_image": d / images, "bits_per_dim": bpd, "time_split": split,
                             "sample": f"one {images}-image chain (batch 1), encode then decode"}}
-    procs = host_procs()
-    pool = ThroughputPool(config, procs)
+    pool = ThroughputPool(config, procs, threads)
     pool.step(999)
     wall, imgs = 0.0, 0
     for i in range(tp_steps):
         w, n = pool.step(i)
         wall += w; imgs += n
     pool.close()
-    out.update(value=imgs * 1024 / wall / 1e6, cores=procs,
-               sample=f"throughput mode: {procs} single-threaded processes x {tp_steps} image(s) each, encode + decode "
+    out.update(value=imgs * 1024 / wall / 1e6, cores=procs * threads,
+               sample=f"throughput mode: {procs} processes x {threads} torch threads x {tp_steps} image(s) each, encode + decode "
                       f"({os.cpu_count()} host cores); latency mode beside it")
     return out
 
@@ -297,7 +305,7 @@ def main():
     ap.add_argument("--config", default="cifar8", help="cifar8 (BASELINE configs[1], default), imagenet4, mnist2, ..., or crop (configs[4])")
     ap.add_argument("--batch", type=int, default=0, help="streams (= images per step) PER GPU (default 1024; imagenet4: 4096)")
     ap.add_argument("--tensor-cores", type=int, default=-1, help="-1 auto, 0 SIMT fp32 convs, 1 tcgen05")
-    ap.add_argument("--ref-procs", type=int, default=0, help="worker processes of the CPU reference arm (0 = one per core)")
+    ap.add_argument("--ref-procs", type=int, default=0, help="worker processes (of 16 threads) of the CPU reference arm (0 = cores / 16)")
     ap.add_argument("--cpu-baseline-images", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="sub-batches coded concurrently on separate CUDA streams (1 = off)")
@@ -596,7 +604,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del codec
         torch.cuda.empty_cache()
-        line["cpu_baseline"] = cpu_baseline_block(args.config, args.cpu_baseline_images, 1)
+        line["cpu_baseline"] = cpu_baseline_block(args.config, args.cpu_baseline_images, 4)
     if world > 1:
         dist.barrier()
     if rank == 0:

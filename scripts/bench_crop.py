@@ -107,10 +107,17 @@ def run_crop(args, rank, world, local):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         gathered = [conts]
-        if world > 1:                                         # rank 0 collects every container (the "gather the final bitstreams" step)
-            gathered = [None] * world
-            dist.all_gather_object(gathered, [c.tobytes() for c in conts])
-            gathered = [[np.frombuffer(b, dtype=np.uint32) for b in g] for g in gathered]
+        if world > 1:                                         # every rank receives every container (the "gather the final bitstreams" step):
+            # one device buffer of container words + lengths per rank, NCCL all_gather_into_tensor (parallel.gather_packed)
+            flat = np.concatenate(conts).view(np.int32) if conts else np.zeros(0, np.int32)
+            words_t = torch.from_numpy(flat.copy()).to(dev) if flat.size else torch.zeros(1, dtype=torch.int32, device=dev)
+            lens_t = torch.tensor([len(c) for c in conts], dtype=torch.int64, device=dev)
+            W, M, counts = parallel.gather_packed(words_t, lens_t, torch.zeros_like(lens_t))
+            Wh, Mh, ch = W.cpu().numpy().view(np.uint32), M.cpu().numpy(), counts.cpu().numpy()
+            gathered = []
+            for r in range(world):
+                off = np.concatenate([[0], np.cumsum(Mh[r, 0, :int(ch[r, 1])])]).astype(np.int64)
+                gathered.append([Wh[r, off[i]:off[i + 1]].copy() for i in range(int(ch[r, 1]))])
         t2 = time.perf_counter()
         back = decompress_images(codec, conts, hwc_quirk=args.hwc_quirk) if my_images else []
         torch.cuda.synchronize()
