@@ -3,13 +3,15 @@
 // pixel level (utils/torch/rand.py:146-147).  Same contract and the same integers as k_rows / k_pop_coarse in ans_rows.cu
 // (ANS.__init__, cifar_compress.py:25-39; ANS.encode/decode :48-67); what differs is how the float64 work is organised:
 //
-//   phase A  k_rows6   one warp per (stream,row).  The plan (rows6_core.cuh) drops the bins whose integer pmf is
-//            provably 1, deals the live bins [kl,kh) to the 32 lanes in consecutive chunks of m, and every lane walks its
-//            chunk with the geometric recurrence u_{k+1} = u_k rho (7 FP64 instructions per bin, no shared memory, no
-//            endpoint loads).  A bin whose fixed-point pmf lands within `win` of a truncation boundary is recomputed with
-//            the exact function bsw_cdf_fast on the real endpoints, so the integers are the exact function's.
+//   phase A  k_rows6   one warp per stream x eight consecutive rows (four lanes per row).  The plan (rows6_core.cuh) drops
+//            the bins whose integer pmf is provably 1 and cuts the live bins [kl,kh) into 32 chunks of m; a lane walks its 8
+//            chunks as ONE chain with the geometric recurrence u_{k+4} = u_k rho^4: per bin one multiply, one scaled
+//            1 + u (FMA), a Newton reciprocal (3 FMAs) and one add that quantises the scaled cdf -- 6 FP64 instructions --
+//            and the pmf is the 64-bit INTEGER difference of two such cdf bit patterns (no shared memory, no endpoint
+//            loads).  A bin whose fixed-point pmf lands within `win` of a truncation boundary is recomputed with the
+//            exact function bsw_cdf_fast on the real endpoints, so the integers are the exact function's.
 //            push: emits (P_s, C_s, M) of the coded symbol (16 B per row).
-//            pop : emits the integer cdf at the start of every lane chunk (32 x 4 B) + (argmax, remnant, kl, kh, m) (8 B).
+//            pop : emits the integer cdf at the start of every chunk (32 x 4 B) + (argmax, remnant, kl, kh, m) (8 B).
 //   phase B  k_pop6    one warp per stream, serial in the head: ballot over the 32 chunk bases -> the chunk, every lane
 //            evaluates ONE bin of it from (t0 + k dt) -- no table, no dependent global load -- scan + ballot -> symbol.
 //            (push: k_push_pairs of ans_rows.cu, unchanged.)
@@ -24,8 +26,7 @@
 
 namespace {
 
-// warps per CTA in phase A (one row index, RW6 streams).  16 x 32 x 64 registers = half an SM's register file, so two of
-// these CTAs fill an SM, or one of them sits beside one k_conv_tc CTA; 12 warps leave the compiler 80 registers.
+// phase A: 16 warps per CTA (16 streams x the same row group), 64 registers per thread -> two CTAs per SM
 constexpr int PW6 = 4;       // warps (= streams) per CTA in phase B
 
 // exact float64 pmf of bin k of the row (what the reference's tensor expression yields, cifar_compress.py:182-184)
@@ -76,11 +77,10 @@ __global__ void k_row_meta(const double *__restrict__ endp, int64_t ers, int64_t
 
 // ---- phase A -------------------------------------------------------------------------------------------------------------
 // One warp = one stream x 32/LPR consecutive rows: LPR lanes share a row, and every lane walks CPL = 32/LPR of the row's 32
-// chunks one after the other (chunks j*CPL .. j*CPL+CPL-1 for lane j of the row).  A chunk is what rows6_core.cuh defines
-// it to be -- m consecutive live bins, anchored by its own exp() and walked with the geometric recurrence -- so the
-// integers do not depend on LPR; what LPR buys is that the per-row work (1/sigma, the plan, exp(-dt), the scan / argmax /
-// remnant epilogue: about as many instructions as a whole 32-bin chunk) is issued once per 32/LPR rows instead of once per
-// row.  LPR = 32 is the one-row-per-warp mapping of the first version of this kernel.
+// chunks (chunks j*CPL .. j*CPL+CPL-1 for lane j of the row: contiguous bins, one chain).  The integers do not depend on
+// LPR -- they are the exact function's either way (asserted by the mapping test and the verify build); what LPR buys is
+// that the per-row work (1/sigma, the plan, two exps, the scan / argmax / remnant epilogue: about as many instructions as
+// 32 bins of the loop) is issued once per 32/LPR rows instead of once per row.  LPR = 32 is one row per warp.
 // vstat (VERIFY builds only): [0] bins whose emitted integer differs from the exact function's, [1] worst
 // |screened - exact| scaled pmf of a bin that was trusted, in thousandths of that row's window (1000 = the error that
 // could flip a truncation), [2] bins checked, [3] bins that took the exact path.
@@ -89,10 +89,11 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
         const float *__restrict__ sc, int64_t sss, const double *__restrict__ endp, int64_t ers,
         const R6RowMeta *__restrict__ meta, int64_t mrs, const int16_t *__restrict__ sym, int bits, int q,
         uint4 *__restrict__ pairs, uint32_t *__restrict__ bases, uint2 *__restrict__ fix, unsigned long long *vstat, int zero,
-        double mult2) {
-    // mult2 = (2^bits - 2^q) * 2^20 (:28; the pmf in 2^-20 fixed point: < 2^51) comes in as an argument: FP64 instructions
-    // read it straight from the constant bank, where a value derived in the kernel was re-derived (2 moves + a DMUL) by
-    // the compiler in every 4-bin group to save two registers.
+        double mult2, double rmult2, double Tone) {
+    // mult2 = (2^bits - 2^q) * 2^20 (:28; the pmf in 2^-20 fixed point: < 2^51), its reciprocal and Tone = mult2 + 1.5 * 2^52
+    // (the quantised cdf of the row's last upper endpoint, cdf = 1: exact) come in as arguments:
+    // FP64 instructions read them straight from the constant bank, where a value derived in the kernel was re-derived
+    // (2 moves + a DMUL) by the compiler in every 4-bin group to save two registers.
     constexpr int RPW = 32 / LPR;                         // rows per warp
     constexpr int CPL = 32 / LPR;                         // chunks per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -110,55 +111,57 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
     }
     int sy = 0;
     if (!POP) sy = (int)sym[(int64_t)si * L + row];
-    auto slow_raw = [&](int k) -> uint32_t {              // the exact function's integer, raw domain
+    auto slow_raw = [&](int k) -> uint32_t {              // the exact function's integer trunc(pmf * mult) (:29)
         const double mult = (double)(((int64_t)1 << bits) - ((int64_t)1 << q));
-        return __double2uint_rz(__dmul_rn(r6_slow_pmf(mu, mss, sc, sss, endp, ers, S, row, si, k), mult)) + 0x80000000u;   // :29 trunc
+        return __double2uint_rz(__dmul_rn(r6_slow_pmf(mu, mss, sc, sss, endp, ers, S, row, si, k), mult));
     };
 
-    // Everything inside the loop stays in the "raw" domain: raw = 2^31 + trunc(pmf * mult) (the magic bit on top), which
-    // orders like P = trunc + 1 (:29, :32) and sums to it modulo 2^32 once 1 - 2^31 per bin is added back at the end.
-    uint32_t rsum = 0, lbest = 0, pre = 0, pv = 0, npre = 0, nbin = 0;
+    // The loop works on raw = trunc(pmf * mult); P = raw + 1 (:29, :32) is restored once per lane at the end.
+    // My bins: chunks j*CPL .. j*CPL+CPL-1 are contiguous, [ks0, kend), walked as ONE chain of 4-bin groups anchored by a
+    // single exp (the 4-step multiplier rho[3] has its own exp, so 64 steps accumulate < 4 of the 64 window units: measured
+    // by the CPU model and by the verify build); chunk boundaries only mark where the pop side's chunk bases are taken.
+    const int ks0 = pl.kl + j * CPL * pl.m;
+    const int kend = min(ks0 + CPL * pl.m, pl.kh);
+    uint32_t rsum = 0, lbest = 0, pre = 0, pv = 0, npre = 0;
+    bool have_pv = false;
     uint32_t bestv[4] = {0u, 0u, 0u, 0u};
-    int bestk = 0;
+    int bestk = ks0;
     uint32_t cpre[CPL];                                   // P-sum of my bins before chunk i (for the chunk bases of the pop side)
-    double rho[4];
-    rho[0] = r6_exp_neg(pl.dt);
-    rho[1] = __dmul_rn(rho[0], rho[0]);
-    rho[2] = __dmul_rn(rho[1], rho[0]);
-    rho[3] = __dmul_rn(rho[1], rho[1]);                   // (chain multiplier: its ~6 ulp are applied m/4 <= 8 times -- measured < 3 of 64 window units)
-    // four registers that just hold `zero` (a kernel argument, so the compiler cannot fold it), see r6_rcp_seed_lo
-    const int zlo[4] = {zero, zero + zero, zero * 3, zero * 5};
-#pragma unroll 1
-    for (int ci = 0; ci < CPL; ++ci) {
-        if (POP) {
-            const uint32_t sofar = rsum - nbin * 0x7fffffffu;
 #pragma unroll
-            for (int t = 0; t < CPL; ++t) if (t == ci) cpre[t] = sofar;
-        }
-        const int ks = pl.kl + (j * CPL + ci) * pl.m;
-        const int ke = min(ks + pl.m, pl.kh);
-        if (ks >= ke) continue;
-        double ub = r6_exp_neg(__fma_rn((double)(ks - 1), pl.dt, pl.t0));       // exp(-t) at the endpoint below the chunk's first bin
-        double prev = ks == 0 ? 0.0 : r6_rcp3(__dadd_rn(1.0, ub));               // lower edge of bin 0 is cdf = 0 (:184)
-        auto group = [&](int k0, auto maybe_last_t, bool last) {
-            double z[4];
-            r6_group<decltype(maybe_last_t)::value>(ub, prev, rho, mult2, pl.magic, z, last, zlo);
-            uint32_t vv[4];
+    for (int t = 0; t < CPL; ++t) cpre[t] = 0u;
+    if (ks0 < kend) {
+        const double rho1 = r6_exp_neg(pl.dt), rho4 = r6_exp_neg(__dmul_rn(4.0, pl.dt));
+        // four registers that just hold `zero` (a kernel argument, so the compiler cannot fold it), see r6_rcp_seed_lo
+        const int zlo[4] = {zero, zero + zero, zero * 3, zero * 5};
+        double ub = r6_exp_neg(__fma_rn((double)(ks0 - 1), pl.dt, pl.t0));       // exp(-t) at the endpoint below my first bin
+        double Tprev = ks0 == 0 ? R6_MAGIC0 : r6_quant(ub, rmult2);             // lower edge of bin 0 is cdf = 0 (:184)
+        int next_chunk = ks0, ci = 0;
+#pragma unroll 2
+        for (int k0 = ks0; k0 < kend; k0 += 4) {
+            if (POP && k0 == next_chunk) {                // chunk boundary: remember the P-sum so far
+                const uint32_t sofar = rsum + (uint32_t)(k0 - ks0);
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) if (t == ci) cpre[t] = sofar;
+                ++ci; next_chunk += pl.m;
+            }
+            uint32_t dlo[4], dhi[4], vv[4];
+            r6_group_q(ub, Tprev, rho1, rho4, rmult2, Tone, k0 + 4 == S, zlo, pl.win, dlo, dhi);
             bool any = false;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                vv[t] = r6_raw(z[t]);
-                any |= r6_doubt(z[t], pl.mask);
+                vv[t] = r6_raw_q(dlo[t], dhi[t]);
+                any |= r6_doubt_q(dlo[t], pl.mask);
             }
-            // (No test for a negative pmf: on an affine row u decreases strictly along the chain, so c can only fail to
-            // increase by reciprocal rounding noise, 2^-53 -- four orders of magnitude inside the window.  Rows the plan
-            // does not vouch for have mask == 0 and take the exact path for every bin.)
+            // (No test for a negative pmf: on an affine row u decreases strictly along the chain, so T can only fail to
+            // increase by rounding noise, one unit -- far inside the window.  Rows the plan does not vouch for have
+            // mask == 0 and take the exact path for every bin.)
             if (VERIFY) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const double ex = r6_slow_pmf(mu, mss, sc, sss, endp, ers, S, row, si, k0 + t);
-                    if (pl.mask != 0u && !r6_doubt(z[t], pl.mask)) {
-                        const double err = fabs((z[t] - pl.magic) - ex * mult2) * 1000.0 / (pl.magic - 6755399441055744.0);
+                    if (pl.mask != 0u && !r6_doubt_q(dlo[t], pl.mask)) {
+                        const double D = (double)(((unsigned long long)dhi[t] << 32) | dlo[t]) - (double)pl.win;
+                        const double err = fabs(D - ex * mult2) * 1000.0 / (double)pl.win;
                         atomicMax(vstat + 1, (unsigned long long)(err < 1e18 ? err + 0.999 : 1e18));
                     }
                     atomicAdd(vstat + 2, 1ULL);
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
             if (any) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    if (r6_doubt(z[t], pl.mask)) {
+                    if (r6_doubt_q(dlo[t], pl.mask)) {
                         vv[t] = slow_raw(k0 + t);
                         if (VERIFY) atomicAdd(vstat + 3, 1ULL);
                     }
@@ -193,28 +196,26 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         if (k0 + t < sy) { pre += vv[t]; ++npre; }
-                        if (k0 + t == sy) pv = vv[t];
+                        if (k0 + t == sy) { pv = vv[t]; have_pv = true; }
                     }
                 }
             }
-        };
-        // The chunk's last group is peeled for EVERY lane (no divergence): in the chunk that ends the row it holds bin S-1,
-        // whose upper cdf is the constant 1 -- a select on one value instead of a second copy of the group.
-        const int klast = ke - 4;
-#pragma unroll 2
-        for (int k0 = ks; k0 < klast; k0 += 4) group(k0, std::false_type{}, false);
-        group(klast, std::true_type{}, ke == S);
-        nbin += (uint32_t)(ke - ks);
+        }
+        if (POP) {                                        // chunks past my last bin: the P-sum of all my bins
+            const uint32_t sofar = rsum + (uint32_t)(kend - ks0);
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) if (t >= ci) cpre[t] = sofar;
+        }
     }
+    const uint32_t nbin = ks0 < kend ? (uint32_t)(kend - ks0) : 0u;
     int lbi = bestk;                                      // first position of the maximum inside its group
 #pragma unroll
     for (int t = 3; t >= 0; --t) if (bestv[t] == lbest) lbi = bestk + t;
-    // back to P = trunc + 1: every bin carries 2^31 - 1 too much
-    const uint32_t lsum = rsum - nbin * 0x7fffffffu;
-    pre -= npre * 0x7fffffffu;
-    const bool have_pv = pv != 0u;                        // (raw values carry the 2^31 bit: never 0)
-    pv -= 0x7fffffffu;
-    lbest = nbin ? lbest - 0x7fffffffu : 0u;
+    // back to P = trunc + 1
+    const uint32_t lsum = rsum + nbin;
+    pre += npre;
+    pv += 1u;
+    lbest = nbin ? lbest + 1u : 0u;
     uint32_t incl = lsum;
 #pragma unroll
     for (int o = 1; o < LPR; o <<= 1) {
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
 #pragma unroll
         for (int t = 0; t < CPL; ++t) {
             const int ks = pl.kl + (j * CPL + t) * pl.m;
-            bs[t] = excl + cpre[t] + ((ks > bi) ? rem : 0u);      // (an empty chunk gets the cdf at kh: above any m the search sends here)
+            bs[t] = excl + cpre[t] + ((ks > bi) ? rem : 0u);      // (a chunk past the live range gets the cdf at kh: above any m the search sends there)
         }
         if (valid) {
             uint32_t *bo = bases + out * 32 + j * CPL;
@@ -465,7 +466,9 @@ int bsw_rows6_launch(int phase, bool pop, bsw_streams *s, int first, int count, 
     k_rows6<POP_, VER_, LPR_><<<dim3((unsigned)((L + 32 / LPR_ - 1) / (32 / LPR_)), (count + 15) / 16), 512, 0, st>>>(            \
         count, L, S, mu, mss, sc, sss, endp, ers, mt, mrs, POP_ ? nullptr : sym, bits, q, POP_ ? nullptr : pairs,                 \
         POP_ ? bases : nullptr, POP_ ? fix : nullptr, VER_ ? g_vstat : nullptr, 0,                                                \
-        (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0)
+        (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0,                                                           \
+        1.0 / ((double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0),                                                     \
+        (double)(((int64_t)1 << bits) - ((int64_t)1 << q)) * 1048576.0 + R6_MAGIC0)
 #define R6_PICK(VER_, LPR_) do { if (pop) { R6_LAUNCH(true, VER_, LPR_); } else { R6_LAUNCH(false, VER_, LPR_); } } while (0)
         if (g_verify) { if (env_lpr == 32) R6_PICK(true, 32); else R6_PICK(true, 4); }
         else if (env_lpr == 32) R6_PICK(false, 32);

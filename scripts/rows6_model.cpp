@@ -1,4 +1,5 @@
-// CPU model of k_rows6 / k_pop6 (bitswap_b200/csrc/rows6_core.cuh): runs the same per-lane arithmetic, 32 lanes in a loop,
+// CPU model of k_rows6 / k_pop6 (bitswap_b200/csrc/rows6_core.cuh): runs the same per-lane arithmetic (quantised 4-bin groups,
+// one chain per lane over its 8 chunks), the row's lanes in a loop,
 // against the exact function on random uniform-grid rows, and checks
 //   (1) every emitted integer pmf == the exact function's, (2) dead bins really have P == 1, (3) the worst screening error
 //   of a trusted bin is far inside the window, (4) the chunk-base / pop search reproduces a search of the full table.
@@ -27,6 +28,8 @@ static double exact_pmf(const double *e, int k, int S, double m, double s, doubl
 }
 static uint64_t rng = 88172645463325252ull;
 static double urand() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (double)(rng >> 11) * (1.0 / 9007199254740992.0); }
+
+constexpr int LPR = 4, CPL = 32 / LPR;      // the kernel's default mapping: 4 lanes per row, 8 chunks per lane
 
 int main(int argc, char **argv) {
     long nrows = argc > 1 ? atol(argv[1]) : 20000;
@@ -68,39 +71,35 @@ int main(int argc, char **argv) {
         R6Plan pl = r6_plan(M, m, rs, S, bits);
         if (pl.mask == 0) ++notok;
         if (pl.kl % 4 || pl.kh % 4 || pl.kl < 0 || pl.kh > S || pl.kh <= pl.kl || pl.m < 4 || pl.m > 32 || 32 * pl.m < pl.kh - pl.kl) { printf("bad plan kl %d kh %d m %d\n", pl.kl, pl.kh, pl.m); return 1; }
+        // k_rows6's walk: LPR lanes share the row, lane j walks chunks j*CPL .. j*CPL+CPL-1 as ONE chain (anchored once)
         uint32_t lsum[32];
-        for (int lane = 0; lane < 32; ++lane) {
-            int ks = pl.kl + lane * pl.m, ke = std::min(ks + pl.m, pl.kh);
-            lsum[lane] = 0;
-            if (ks >= ke) continue;
-            double ub = r6_exp_neg(fma((double)(ks - 1), pl.dt, pl.t0));
-            double prev = ks == 0 ? 0.0 : r6_rcp3(1.0 + ub);
-            double rho[4] = {r6_exp_neg(pl.dt), 0, 0, 0};
-            rho[1] = rho[0] * rho[0]; rho[2] = rho[1] * rho[0]; rho[3] = rho[1] * rho[1];
-            auto group = [&](int k0, bool last) {
-                double z[4];
-                r6_group<true>(ub, prev, rho, mult2, pl.magic, z, last, {0, 0, 0, 0});
-                uint32_t mn = 0xffffffffu; bool any = false; uint32_t vv[4];
-                for (int t = 0; t < 4; ++t) { uint32_t raw = r6_raw(z[t]); any |= r6_doubt(z[t], pl.mask); mn = std::min(mn, raw); vv[t] = raw + 0x80000001u; }
+        for (int c = 0; c < 32; ++c) lsum[c] = 0;
+        const double a = 1.0 / mult2, Tone = mult2 + R6_MAGIC0;
+        const double rho1 = r6_exp_neg(pl.dt), rho4 = r6_exp_neg(4.0 * pl.dt);
+        for (int j = 0; j < LPR; ++j) {
+            const int ks0 = pl.kl + j * CPL * pl.m, kend = std::min(ks0 + CPL * pl.m, pl.kh);
+            if (ks0 >= kend) continue;
+            double ub = r6_exp_neg(fma((double)(ks0 - 1), pl.dt, pl.t0));
+            double Tprev = ks0 == 0 ? R6_MAGIC0 : r6_quant(ub, a);
+            for (int k0 = ks0; k0 < kend; k0 += 4) {
+                uint32_t dlo[4], dhi[4], vv[4];
+                r6_group_q(ub, Tprev, rho1, rho4, a, Tone, k0 + 4 == S, {0, 0, 0, 0}, pl.win, dlo, dhi);
+                bool any = false;
+                for (int t = 0; t < 4; ++t) { vv[t] = r6_raw_q(dlo[t], dhi[t]) + 1u; any |= r6_doubt_q(dlo[t], pl.mask); }
                 for (int t = 0; t < 4; ++t) {
                     ++evaluated;
-                    if (pl.mask != 0 && !r6_doubt(z[t], pl.mask) && mn >= 0x80000000u) {
-                        double err = fabs((z[t] - pl.magic) - exact_pmf(e.data(), k0 + t, S, m, s, rs) * mult2);
+                    if (pl.mask != 0 && !r6_doubt_q(dlo[t], pl.mask)) {
+                        const double D = (double)(((uint64_t)dhi[t] << 32) | dlo[t]) - (double)pl.win;
+                        double err = fabs(D - exact_pmf(e.data(), k0 + t, S, m, s, rs) * mult2);
                         worst = fmax(worst, err);
-                        double win = pl.magic - 6755399441055744.0;
-                        worst_frac = fmax(worst_frac, err / win);
-                        if (win == 64.0) worst64 = fmax(worst64, err);
+                        worst_frac = fmax(worst_frac, err / (double)pl.win);
+                        if (pl.win == 64u) worst64 = fmax(worst64, err);
                     }
                 }
-                if (any || mn < 0x80000000u) {
-                    bool all = mn < 0x80000000u;
-                    for (int t = 0; t < 4; ++t) if (all || r6_doubt(z[t], pl.mask)) { vv[t] = (uint32_t)(long long)(exact_pmf(e.data(), k0 + t, S, m, s, rs) * mult) + 1u; ++doubted; }
-                }
-                for (int t = 0; t < 4; ++t) { P[k0 + t] = vv[t]; lsum[lane] += vv[t]; }
-            };
-            int klast = ke - 4;
-            for (int k0 = ks; k0 < klast; k0 += 4) group(k0, false);
-            group(klast, ke == S);
+                if (any)
+                    for (int t = 0; t < 4; ++t) if (r6_doubt_q(dlo[t], pl.mask)) { vv[t] = (uint32_t)(long long)(exact_pmf(e.data(), k0 + t, S, m, s, rs) * mult) + 1u; ++doubted; }
+                for (int t = 0; t < 4; ++t) { P[k0 + t] = vv[t]; lsum[(k0 + t - pl.kl) / pl.m] += vv[t]; }
+            }
         }
         for (int k = 0; k < S; ++k) {
             ++bins;
