@@ -194,8 +194,9 @@ def _tp_init(config, threads):
 class ThroughputPool:
     """All host cores on the reference's CPU path (throughput mode): `procs` worker processes of `threads`
     torch threads each, procs x threads = cores, every worker its own chain.  16 threads per chain is where the path's torch
-    ops stop scaling; one single-threaded process per core was measured too (profiles/bench_r2_reference_arm_1thread.json:
-    0.0026 Mpixel/s on 128 cores, 45 s per image -- a 25-step arm would take 20 minutes)."""
+    ops stop scaling for one chain.  One single-threaded process per core was measured too and is the stronger aggregate
+    (profiles/bench_r2_reference_arm_1thread.json: 0.0026 against 0.0018 Mpixel/s on 128 cores) but needs 48 s per image,
+    i.e. 20 minutes for the 25-step arm the driver launches; the line says so (`single_thread_per_core`)."""
 
     def __init__(self, config, procs, threads):
         import multiprocessing as mp
@@ -257,7 +258,9 @@ def run_reference_arm(args, cfg, rank, world):
             "latency_mode": {"threads": threads, "encode_s_per_image": e / 2, "decode_s_per_image": d / 2,
                              "Mpixel_s": 2 * 1024 / (e + d) / 1e6, "time_split": split,
                              "sample": "one 2-image chain alone on the box"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs * threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs * threads, "kind": "port", "sample": sample,
+                             "single_thread_per_core": "measured once on this pool's 128-core host: 0.0026 Mpixel/s, 48 s per step "
+                                                       "(profiles/bench_r2_reference_arm_1thread.json) -- 1.45x this arm's rate"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -280,6 +283,8 @@ def cpu_baseline_block(config, images, tp_steps):
         wall += w; imgs += n
     pool.close()
     out.update(value=imgs * 1024 / wall / 1e6, cores=procs * threads,
+               single_thread_per_core="measured once on this pool's 128-core host: 0.0026 Mpixel/s "
+                                      "(profiles/bench_r2_reference_arm_1thread.json)",
                sample=f"throughput mode: {procs} processes x {threads} torch threads x {tp_steps} image(s) each, encode + decode "
                       f"({os.cpu_count()} host cores); latency mode beside it")
     return out
@@ -604,7 +609,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del codec
         torch.cuda.empty_cache()
-        line["cpu_baseline"] = cpu_baseline_block(args.config, args.cpu_baseline_images, 4)
+        line["cpu_baseline"] = cpu_baseline_block(args.config, args.cpu_baseline_images, 3)
     if world > 1:
         dist.barrier()
     if rank == 0:
