@@ -76,7 +76,11 @@ def facts(streams, out, paths):
     import re
     acc = {}
     for path in paths:
-        label = "ncu --set full --clock-control none, " + os.path.basename(path) + " (summary: profiles/r2_ncu_final.md)"
+        only = None
+        if ":" in path:                                   # report.ncu-rep:cat1,cat2 -> take only these categories from it
+            path, only = path.split(":", 1)
+            only = set(only.split(","))
+        label = "ncu --set full --clock-control none, " + os.path.basename(path) + " (summaries: profiles/r2_ncu_final*.md)"
         txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr = rows[0]
@@ -90,7 +94,7 @@ def facts(streams, out, paths):
             ms_ = col(r, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(
                 units[hdr.index("gpu__time_duration.sum")].replace("second", "s").replace("msecond", "ms").replace("usecond", "us").replace("nsecond", "ns"), 1.0)
             for cat, rx, want_gx in CATS:
-                if not re.search(rx, name):
+                if not re.search(rx, name) or (only is not None and cat not in only):
                     continue
                 if isinstance(want_gx, int) and gx != want_gx:
                     continue
