@@ -7,12 +7,13 @@ mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $O/smi.txt
 python -m pytest tests -m gpu -q 2>&1 | tail -8 > $O/pytest.txt
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1
-python bench.py --steps 5 --warmup 3 > $O/bench_cifar8.json 2> $O/bench_cifar8.err
+python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_cifar8.json 2> $O/bench_cifar8.err
 python bench.py --steps 3 --warmup 3 --lanes 1 --no-cpu-baseline > $O/bench_cifar8_lanes1.json 2> $O/bench_cifar8_lanes1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 1000 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 1 --lanes 1 --no-cpu-baseline > $O/launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_rows6|k_pop6|k_push_pairs|k_conv_tc|k_rows<|k_pop_coarse' -s 40 -c 24 -o $O/r2_final python bench.py --steps 1 --warmup 1 --lanes 1 --no-cpu-baseline > $O/ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_rows6|k_pop6|k_push_pairs|k_conv_tc|k_rows<|k_pop_coarse' -s 2 -c 40 -o $O/r2_final python bench.py --steps 1 --warmup 1 --lanes 1 --no-cpu-baseline > $O/ncu.log 2>&1
 python bench.py --config imagenet4 --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_imagenet4.json 2> $O/bench_imagenet4.err
 python bench.py --config mnist2 --steps 3 --warmup 3 --no-cpu-baseline > $O/bench_mnist2.json 2> $O/bench_mnist2.err
 python bench.py --config crop --steps 1 --warmup 1 > $O/bench_crop_1gpu.json 2> $O/bench_crop_1gpu.err
-timeout 400 python bench.py --impl reference --steps 1 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
+python bench.py --config crop --steps 1 --warmup 1 --crop-images 16 --hwc-quirk > $O/bench_crop_hwc_quirk_16.json 2> $O/bench_crop_hwc_quirk_16.err
+timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
 ls -la $O
