@@ -51,8 +51,16 @@ def launches(path, out):
             f.write(f"| `{k}` | {cnt[k]} | {tot[k]:.2f} | {tot[k]/cnt[k]:.3f} | {100*tot[k]/total:.1f}% |\n")
 
 
+def raw_csv(path):
+    """--page raw --csv of a report; a path ending in .csv is taken as that export already (made on the GPU box when the
+    .ncu-rep itself is too large to bring back)."""
+    if path.endswith(".csv"):
+        return open(path).read()
+    return subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+
+
 def full(path, out):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    txt = raw_csv(path)
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(out, "w") as f:
@@ -81,7 +89,7 @@ def facts(streams, out, paths):
             path, only = path.split(":", 1)
             only = set(only.split(","))
         label = "ncu --set full --clock-control none, " + os.path.basename(path) + " (summaries: profiles/r2_ncu_final*.md)"
-        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+        txt = raw_csv(path)
         rows = list(csv.reader(txt.splitlines()))
         hdr = rows[0]
 
