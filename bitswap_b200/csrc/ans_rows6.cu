@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(PW6 * 32) k_pop6(bsw_streams sv, int first, in
     float mu_w = 0.f, sc_w = 1.f, mu_nx, sc_nx;
     uint2 fx_w = make_uint2(0, 0), fx_nx;
     double a_nx, d_nx, dev_nx;
-    double t0_w = 0.0, dt_w = 1.0, rs_w = 1.0, magic_w = 0.0, rho_w = 1.0;
+    double t0_w = 0.0, dt_w = 1.0, rs_w = 1.0, magic_w = 0.0;
     uint32_t dmask_w = 0;
     auto load_block = [&](int64_t r0) {
         const int64_t r = r0 + lane;
@@ -355,30 +355,17 @@ __global__ void __launch_bounds__(PW6 * 32) k_pop6(bsw_streams sv, int first, in
         M.a = a_nx; M.d = d_nx; M.dev = dev_nx; M.rsv = 0.0;
         const R6Plan pl = r6_plan(M, (double)mu_w, rs_w, S, bits);
         t0_w = pl.t0; dt_w = pl.dt; magic_w = pl.magic; dmask_w = pl.mask;
-        rho_w = r6_exp_neg(pl.dt);
-    };
-    // Head-independent values of ONE row, per lane, so that nothing but a product stands between the chunk index (known only
-    // once the head is) and the bin's cdf: Uc = exp(-t) at the endpoint below the first bin of chunk `lane`, Rl = rho^lane.
-    // Bin k = kl + chunk m + lane then has u_lo = Uc[chunk] Rl below it and u_hi = u_lo rho above it.  They are computed
-    // one row ahead (row jr of the current block), where the two exps fill issue slots the serial chain leaves empty.
-    auto precompute = [&](int jr, double &U, double &R) {
-        const double t0 = shfl_d(t0_w, jr), dt = shfl_d(dt_w, jr);
-        const uint32_t fx = __shfl_sync(FULL, fx_w.x, jr);
-        const int kl = (int)((fx >> 10) & 255u) << 2, m = (int)((fx >> 27) & 15u) << 2;
-        U = r6_exp_neg(__fma_rn((double)(kl + lane * m - 1), dt, t0));
-        R = r6_exp_neg(__dmul_rn((double)lane, dt));
     };
     load_block((L - 1) & ~(int64_t)31);
     int my_sym = 0;
-    double Uc = 0.0, Rl = 0.0, Uc_n = 0.0, Rl_n = 0.0;
     // chunk bases are independent of the head: keep the loads two rows ahead of their use
     uint32_t base_n1 = __ldg(bb + (L - 1) * 32 + lane);
     uint32_t base_n2 = L > 1 ? __ldg(bb + (L - 2) * 32 + lane) : 0u;
     for (int64_t i = L - 1; i >= 0; --i) {
         const int j32 = (int)(i & 31);
         const bool new_block = (j32 == 31 || i == L - 1);
-        if (new_block) { adopt_block(); load_block((i & ~(int64_t)31) - 32); precompute(j32, Uc, Rl); }
-        const double magic = shfl_d(magic_w, j32), rho = shfl_d(rho_w, j32);
+        if (new_block) { adopt_block(); load_block((i & ~(int64_t)31) - 32); }
+        const double t0 = shfl_d(t0_w, j32), dt = shfl_d(dt_w, j32), magic = shfl_d(magic_w, j32);
         const uint32_t dmask = __shfl_sync(FULL, dmask_w, j32);
         const uint32_t fx = __shfl_sync(FULL, fx_w.x, j32), rem = __shfl_sync(FULL, fx_w.y, j32);
         const int bi = (int)(fx & 1023u), kl = (int)((fx >> 10) & 255u) << 2, kh = (int)((fx >> 18) & 511u) << 2, m = (int)((fx >> 27) & 15u) << 2;
@@ -387,40 +374,38 @@ __global__ void __launch_bounds__(PW6 * 32) k_pop6(bsw_streams sv, int first, in
         if (i > 1) base_n2 = __ldg(bb + (i - 2) * 32 + lane);
         const uint32_t mm = (uint32_t)ws.x & mask;                                       // cifar_compress.py:60
         const uint32_t Ckh = (1u << bits) - (uint32_t)(S - kh);                          // integer cdf at bin kh (dead bins: P = 1)
-        // dead bins (P = 1 each): on the left C[k] = k, on the right C[k] = Ckh + (k - kh).  The live search below runs
-        // unconditionally (one basic block for the scheduler) and is overridden by a select.
-        const bool dead_l = mm < (uint32_t)kl, dead_r = mm >= Ckh, dead = dead_l || dead_r;
-        const int chunk = max(31 - __clz(__ballot_sync(FULL, base <= mm)), 0);          // chunks past the live range hold Ckh > mm
-        if (j32 > 0) precompute(j32 - 1, Uc_n, Rl_n);                                    // next row's values: independent of the head
-        const int k = kl + chunk * m + lane;
-        const bool active = lane < m && k < kh;
-        const double u_lo = __dmul_rn(shfl_d(Uc, chunk), Rl);                            // exp(-t) at my bin's lower endpoint
-        const double u_hi = __dmul_rn(u_lo, rho);                                        //           ... upper endpoint
-        const double c_hi = (k >= S - 1) ? 1.0 : r6_rcp3(__dadd_rn(1.0, u_hi));
-        const double c_lo = (k <= 0) ? 0.0 : r6_rcp3(__dadd_rn(1.0, u_lo));
-        const double z = __fma_rn(__dsub_rn(c_hi, c_lo), mult2, magic);
-        uint32_t raw = r6_raw(z);
-        const bool doubt = active && !dead && (r6_doubt(z, dmask) || raw < 0x80000000u);
-        if (__any_sync(FULL, doubt)) {                                                   // rare: the exact function on the real endpoints
-            const double m_ = (double)__shfl_sync(FULL, mu_w, j32), s_ = (double)__shfl_sync(FULL, sc_w, j32);
-            const double rs = shfl_d(rs_w, j32);
-            if (doubt) raw = r6_exact_pm(endp + i * ers, k, S, m_, s_, rs, mult) + 0x80000000u;
+        uint32_t ps, cs;
+        int s;
+        if (mm < (uint32_t)kl) { s = (int)mm; ps = 1u; cs = mm; }                        // dead bins on the left: C[k] = k
+        else if (mm >= Ckh) { s = kh + (int)(mm - Ckh); ps = 1u; cs = mm; }              // dead bins on the right
+        else {
+            const int chunk = 31 - __clz(__ballot_sync(FULL, base <= mm));              // empty chunks hold Ckh > mm
+            const int k = kl + chunk * m + lane;
+            const bool active = lane < m && k < kh;
+            const double th = __fma_rn((double)k, dt, t0);                               // t at my bin's upper endpoint
+            const double c_hi = (k >= S - 1) ? 1.0 : r6_rcp3(__dadd_rn(1.0, r6_exp_neg(th)));
+            const double c_lo = (k <= 0) ? 0.0 : r6_rcp3(__dadd_rn(1.0, r6_exp_neg(__dsub_rn(th, dt))));
+            const double z = __fma_rn(__dsub_rn(c_hi, c_lo), mult2, magic);
+            uint32_t raw = r6_raw(z);
+            const bool doubt = active && (r6_doubt(z, dmask) || raw < 0x80000000u);
+            if (__any_sync(FULL, doubt)) {                                               // rare: the exact function on the real endpoints
+                const double m_ = (double)__shfl_sync(FULL, mu_w, j32), s_ = (double)__shfl_sync(FULL, sc_w, j32);
+                const double rs = shfl_d(rs_w, j32);
+                if (doubt) raw = r6_exact_pm(endp + i * ers, k, S, m_, s_, rs, mult) + 0x80000000u;
+            }
+            const uint32_t v = active ? (raw + 0x80000001u) + (k == bi ? rem : 0u) : 0u;  // :29 trunc, :32 +1, :35 remnant
+            uint32_t incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t cex = __shfl_sync(FULL, base, chunk) + incl - v;              // integer cdf at my bin
+            const int js = 31 - __clz(__ballot_sync(FULL, active && cex <= mm));         // :61 searchsorted 'right' - 1
+            ps = __shfl_sync(FULL, v, js); cs = __shfl_sync(FULL, cex, js);
+            s = kl + chunk * m + js;
         }
-        const uint32_t v = active ? (raw + 0x80000001u) + (k == bi ? rem : 0u) : 0u;      // :29 trunc, :32 +1, :35 remnant
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const uint32_t cex = __shfl_sync(FULL, base, chunk) + incl - v;                  // integer cdf at my bin
-        const int js = 31 - __clz(__ballot_sync(FULL, active && cex <= mm));             // :61 searchsorted 'right' - 1
-        uint32_t ps = __shfl_sync(FULL, v, js), cs = __shfl_sync(FULL, cex, js);
-        int s = kl + chunk * m + js;
-        if (dead) { ps = 1u; cs = mm; s = dead_l ? (int)mm : kh + (int)(mm - Ckh); }
         if (lane == j32) my_sym = s;                                                     // :62
         ws.decode(ps, cs, mm, bits, lane);                                               // :63-65
-        if (j32 > 0) { Uc = Uc_n; Rl = Rl_n; }
         if (j32 == 0 || ws.err) {
             const int64_t r = (i & ~(int64_t)31) + lane;
             if (r < L && r >= i) sy[r] = (int16_t)my_sym;
