@@ -85,6 +85,8 @@ class BitSwapCodec:
         """Pops one image from each stream; returns uint8 CUDA tensor [count, C, 32, 32]. Async."""
         if out is None:
             out = torch.empty((count,) + tuple(self.cfg.xs), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        if not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= count * int(np.prod(self.cfg.xs))):
+            raise ValueError("decode(out=...): need a contiguous uint8 CUDA tensor with room for `count` images")
         self._same_device(streams, out)
         with on_device(self.device):
             check(lib().bsw_codec_decode(self._h, streams.handle, first, count, out.data_ptr(), scheme, cuda_stream_ptr()))
