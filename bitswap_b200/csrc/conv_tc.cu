@@ -653,6 +653,250 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__
     }
 }
 
+// Pair-tile variant: a 2-CTA cluster (one SM pair) owns one IMAGE and issues cta_group::2 MMAs with M = 256, N = 256.
+//   * Why: the convs are bound by L2 -> SM delivery, ~6300 B/clk chip-wide = 42.6 B/clk/SM (B300_MICROARCH.md, "LTS
+//     throughput cap", the same for TMA and LDG).  k_conv_tc fills 48 KB per k-block of twelve 64-cycle MMAs: 48 KB / 42.6 =
+//     1154 cycles against a tensor floor of 768 -- measured 1170.  The half-image tiles fill 32 KB per six MMAs: 769 against
+//     384 -- measured 768.  With N = 256 the activation tile is fetched once per 256 output channels, and with cta_group::2
+//     the weight tile is SPLIT across the pair (128 of its 256 rows each): 32 KB per CTA and k-block of six 128-cycle MMAs
+//     = 769 cycles of L2 against 768 of tensor pipe -- balanced; measured 855 (38 B/clk/SM, 0.90 of either bound).
+//   * CTA r holds image rows 8r..8r+7 (its 128 pixels) of the A tile and weight rows 128r..128r+127 of the B tile; its
+//     accumulators are 128 lanes x {main, cross} x 256 columns = all 512 TMEM columns: no ping-pong, so the epilogue
+//     first empties TMEM into shared memory and registers, hands it back, and does its global traffic under the next tile.
+//   * Leader (cluster rank 0) issues the MMAs and owns the `full` barriers (both CTAs' TMA loads signal them:
+//     cp.async.bulk.tensor ... cta_group::2 with the barrier address' peer bit cleared); tcgen05.commit multicasts to both CTAs'
+//     `empty` and `accf` barriers; the epilogue warps of both CTAs arrive on the leader's `acce` barrier.
+//   * k order, MMA order per accumulator and the epilogue arithmetic are those of the other kernels: bit-identical results.
+constexpr int P2_WTILE = 128 * BK * 2;                         // my 128 of the tile's 256 weight rows: 8 KB per plane
+constexpr int P2_STAGE = 2 * H_TILE_BYTES + 2 * P2_WTILE;      // 32 KB
+constexpr int P2_NSTAGE = 4;
+constexpr int P2_NE = 8;                                       // epilogue warps per CTA: 2 per TMEM lane quadrant, 128 columns each
+constexpr int P2_SCRATCH = P2_NE * 3 * 32 * 32 * 4;            // three 32 x 32 float tiles per epilogue warp (96 KB): see the epilogue
+constexpr int P2_SMEM_BYTES = P2_NSTAGE * P2_STAGE + P2_SCRATCH + 1024 + 256;
+constexpr uint32_t IDESC_2SM = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);   // M = 256, N = 256
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                    // clears the bit that tells the pair's two shared windows apart
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads of the pair: data into MY shared memory, completion bytes onto the LEADER's mbarrier
+__device__ __forceinline__ void tma2_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(0x1000000000000000ull) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "l"(0x1000000000000000ull) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC_2SM), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t *bar) {       // arrives on BOTH CTAs' barrier at this offset
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) { // arrive on the leader CTA's barrier at this offset
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((2 + P2_NE) * 32, 1)
+k_conv_tc_2sm(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
+              const __grid_constant__ CUtensorMap wmap_hi, const __grid_constant__ CUtensorMap wmap_lo, TcArgs a, int ntiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float *scratch = reinterpret_cast<float *>(smem + P2_NSTAGE * P2_STAGE);
+    uint64_t *full_bar = (uint64_t *)(smem + P2_NSTAGE * P2_STAGE + P2_SCRATCH);
+    uint64_t *empty_bar = full_bar + P2_NSTAGE;
+    uint64_t *accf_bar = empty_bar + P2_NSTAGE;          // [2] accumulator buffer complete (leader's MMAs -> both epilogues)
+    uint64_t *acce_bar = accf_bar + 2;                   // [2] accumulator buffer drained  (both epilogues -> leader's MMA thread)
+    uint32_t *tmem_ptr = (uint32_t *)(acce_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_rank();                // 0 = leader
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int nkb = a.taps * a.cchunks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap_lo) : "memory");
+        for (int s = 0; s < P2_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accf_bar[0], 1); mbar_init(&acce_bar[0], 2 * P2_NE);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {     // the pair's TMEM: 512 columns in both CTAs (same warp in both CTAs, same shared offset)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                  // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {     // ===== TMA producer (both CTAs): my half of A, my 64 weight rows =====
+            const int r = a.ks / 2;
+            int stage = 0, phase = 0;
+            for (int t = pair; t < ntiles; t += npairs) {
+                const int img = t;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    int tap = kb / a.cchunks, c0 = (kb - tap * a.cchunks) * BK;
+                    int dy = tap / a.ks, dx = tap - dy * a.ks;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * P2_STAGE;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * P2_STAGE);       // both CTAs' bytes land on the leader's barrier
+                    tma2_load_4d(st, &amap_hi, &full_bar[stage], c0, dx - r, dy - r + 8 * rank, img);
+                    tma2_load_4d(st + H_TILE_BYTES, &amap_lo, &full_bar[stage], c0, dx - r, dy - r + 8 * rank, img);
+                    tma2_load_3d(st + 2 * H_TILE_BYTES, &wmap_hi, &full_bar[stage], c0, 128 * rank, tap);
+                    tma2_load_3d(st + 2 * H_TILE_BYTES + P2_WTILE, &wmap_lo, &full_bar[stage], c0, 128 * rank, tap);
+                    if (++stage == P2_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {     // ===== MMA issuer: the leader, for the pair =====
+            int stage = 0, phase = 0, it = 0;
+            for (int t = pair; t < ntiles; t += npairs, ++it) {
+                mbar_wait(&acce_bar[0], (it & 1) ^ 1);               // both CTAs' epilogues have drained the accumulators (first tile: passes)
+                tc_fence_after();
+                const uint32_t d_main = tmem_base, d_cross = tmem_base + 256;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    uint32_t sbase = smem_u32(smem + stage * P2_STAGE);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        uint64_t a_hi = make_desc_sw64(sbase + kk * 32);
+                        uint64_t a_lo = make_desc_sw64(sbase + H_TILE_BYTES + kk * 32);
+                        uint64_t b_hi = make_desc_sw64(sbase + 2 * H_TILE_BYTES + kk * 32);
+                        uint64_t b_lo = make_desc_sw64(sbase + 2 * H_TILE_BYTES + P2_WTILE + kk * 32);
+                        umma2_bf16(d_main, a_hi, b_hi, (kb | kk) != 0);
+                        umma2_bf16(d_cross, a_lo, b_hi, (kb | kk) != 0);
+                        umma2_bf16(d_cross, a_hi, b_lo, 1);
+                    }
+                    umma2_commit(&empty_bar[stage]);                 // frees the stage in both CTAs when these MMAs retire
+                    if (++stage == P2_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                umma2_commit(&accf_bar[0]);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, my 128 pixels x 256 channels) =====
+        // Phase 1 (exposed, short): main + cross summed out of TMEM -- three of my four 32-channel chunks into my shared
+        // tiles, the fourth kept in registers -- then the accumulators go back to the leader's MMA thread.
+        // Phase 2 (under the next tile's MMAs): bias, residual (loaded one chunk ahead), ELU, bf16 hi/lo split and the
+        // coalesced global stores, chunk by chunk out of shared memory; the register chunk goes through tile 0 once that is done.
+        // float4 i of row r sits at slot i ^ (r & 7) of its 128-byte row: conflict-free both ways without padding, which is
+        // what lets 96 KB of tiles sit next to four 32 KB stages.  (With the whole 128 KB output tile in shared memory only
+        // three stages fit, and the main loop slowed by more than the epilogue saved: profiles/r2_ab_runs.md.)
+        constexpr int CW = 256 / (P2_NE / 4);            // columns per warp: 128 = four chunks
+        static_assert(CW == 128, "epilogue written for four chunks per warp");
+        const int ew = warp - 2;
+        const int cpart = ew >> 2;                       // which CW of the 256 columns
+        const int quad = warp & 3;
+        float *slice = scratch + ew * (3 * 32 * 32);
+        const int rsub = lane >> 3, col4 = (lane & 7) * 4;
+        int it = 0;
+        for (int t = pair; t < ntiles; t += npairs, ++it) {
+            const int img = t;
+            const int64_t pbase = ((int64_t)img * 256 + rank * 128 + quad * 32 + rsub) * 256 + cpart * CW + col4;   // + (4 k) * 256 + cc
+            float4 q[8], qn[8];
+            float s3[32];
+            auto load_resid = [&](float4 (&dst)[8], int cc) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    dst[k] = a.resid ? *reinterpret_cast<const float4 *>(a.resid + pbase + (int64_t)(4 * k) * 256 + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            load_resid(q, 0);
+            mbar_wait(&accf_bar[0], it & 1);
+            tc_fence_after();
+            const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + cpart * CW;
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {
+                uint32_t rr[32], rc[32];
+                tmem_ld32(tb + c * 32, rr);
+                tmem_ld32(tb + 256 + c * 32, rc);
+                float *trow = slice + c * 1024 + lane * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4 *>(trow + ((i ^ (lane & 7)) << 2)) =
+                        make_float4(__uint_as_float(rr[4 * i]) + __uint_as_float(rc[4 * i]),
+                                    __uint_as_float(rr[4 * i + 1]) + __uint_as_float(rc[4 * i + 1]),
+                                    __uint_as_float(rr[4 * i + 2]) + __uint_as_float(rc[4 * i + 2]),
+                                    __uint_as_float(rr[4 * i + 3]) + __uint_as_float(rc[4 * i + 3]));
+            }
+            {
+                uint32_t rr[32], rc[32];
+                tmem_ld32(tb + 96, rr);
+                tmem_ld32(tb + 256 + 96, rc);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s3[i] = __uint_as_float(rr[i]) + __uint_as_float(rc[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&acce_bar[0]);     // the pair's next tile may start
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int cc = c * 32, c0 = cpart * CW + cc;
+                const float *tl = slice + (c < 3 ? c : 0) * 1024;
+                if (c == 3) {                             // the register chunk takes over tile 0 (its readers are done: same warp)
+                    __syncwarp();
+                    float *trow = slice + lane * 32;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4 *>(trow + ((i ^ (lane & 7)) << 2)) = make_float4(s3[4 * i], s3[4 * i + 1], s3[4 * i + 2], s3[4 * i + 3]);
+                    __syncwarp();
+                }
+                if (c < 3) load_resid(qn, cc + 32);
+                const float4 bq = __ldg(reinterpret_cast<const float4 *>(a.bias + c0 + col4));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = 4 * k + rsub;
+                    const int64_t prow = pbase + (int64_t)(4 * k) * 256 + cc;
+                    float4 x = *reinterpret_cast<const float4 *>(tl + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
+                    x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;      // (main+cross)+bias
+                    if (a.resid) { x.x += q[k].x; x.y += q[k].y; x.z += q[k].z; x.w += q[k].w; }
+                    if (a.T_elu) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+                    if (a.T) *reinterpret_cast<float4 *>(a.T + prow) = x;
+                    if (a.A_hi) {
+                        float y[4] = {x.x, x.y, x.z, x.w};
+                        uint32_t hi[2], lo[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float x0 = a.A_elu ? elu1(y[2 * i]) : y[2 * i], x1 = a.A_elu ? elu1(y[2 * i + 1]) : y[2 * i + 1];
+                            __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                            __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                            hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        *reinterpret_cast<uint2 *>(a.A_hi + prow) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2 *>(a.A_lo + prow) = make_uint2(lo[0], lo[1]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) q[k] = qn[k];
+            }
+            __syncwarp();                                 // the tiles are rewritten by my next tile
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    cluster_sync_all();                                  // the peer may signal my barriers / read my shared memory until here
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // mu/sigma heads on the tensor cores: the 3x3 W -> (n_mu + n_sc <= 32) convolution that ends every net
 // (cifar_train.py:349,368,411,426), with the scale transforms and the UnSqueeze2d index map of the x head in the epilogue.
 // GEMM per image: M = 256 pixels (two UMMA M=128 halves), N = 32 (output channels zero-padded), K = taps x 256.
@@ -935,6 +1179,8 @@ int bsw_model_tc_prepare(bsw_model *m) {
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_h, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+    bsw_prefer_max_shared(k_conv_tc_2sm);
     BSW_CUDA(cudaFuncSetAttribute(k_conv_tc_head, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM_BYTES));
     bsw_prefer_max_shared(k_conv_tc_head);
     // one SM-wide L1/shared split for every kernel of the path (see bsw_prefer_max_shared)
@@ -972,17 +1218,19 @@ int bsw_tc_split(bsw_model *m, const float *in, int which, int64_t n, cudaStream
     return BSW_OK;
 }
 
-// Which convs run on the persistent kernel k_conv_tc_p: a bit mask -- 1 = dense 3x3, 2 = dense 5x5 (and larger), 4 = in-convs.
-// Default 0 (BSW_TC_PERSIST overrides): measured on B200 at 1024 images the per-tile grids win or tie once their epilogue is
-// coalesced (the persistent kernel's half-image tiles fetch the weight tile twice, and the convs are bound by L2->SM bytes per
-// MMA and by the power cap, not by the exposed epilogue).  Results are bit-identical either way.
+// Which kernel the dense convs and in-convs run on: a bit mask -- 8 / 16 = dense 3x3 / 5x5 on the pair-tile kernel
+// k_conv_tc_2sm, 1 / 2 = dense 3x3 / 5x5 on the persistent half-image kernel k_conv_tc_p, 4 = in-convs on k_conv_tc_p; a
+// clear bit means the per-tile grid (k_conv_tc / k_conv_tc_h).  Default 24 (BSW_TC_PERSIST overrides): measured on B200 at
+// 1024 images the pair tiles win (3x3 0.83 -> 0.68 ms, 5x5 1.94 -> 1.55 ms) because the convs are bound by L2 -> SM bytes
+// per MMA, which N = 256 and the weight-tile split halve; the half-image tiles of k_conv_tc_p lose to the per-tile grids
+// for the same reason.  Results are bit-identical in every mode.
 static int g_tc_mode = -1;
 static bool tc_persistent(int which) {
-    static const int env = getenv("BSW_TC_PERSIST") ? atoi(getenv("BSW_TC_PERSIST")) : 0;
+    static const int env = getenv("BSW_TC_PERSIST") ? atoi(getenv("BSW_TC_PERSIST")) : 24;
     return (((g_tc_mode < 0) ? env : g_tc_mode) & which) != 0;
 }
 extern "C" int bsw_set_conv_mode(int mode) {
-    BSW_REQUIRE(mode >= -1 && mode <= 7, "bsw_set_conv_mode: -1 (default) or a mask of 1 (dense 3x3) | 2 (dense 5x5) | 4 (in-convs)");
+    BSW_REQUIRE(mode >= -1 && mode <= 31, "bsw_set_conv_mode: -1 (default) or a mask of 1 | 2 | 4 (persistent: dense 3x3, 5x5, in-convs) | 8 | 16 (pair tiles: dense 3x3, 5x5)");
     g_tc_mode = mode;
     return BSW_OK;
 }
@@ -1011,12 +1259,15 @@ int bsw_conv_tc(bsw_model *m, const ConvSlot &c, const ConvArgs &a, int64_t n, c
     t.A_hi = a.A_planes >= 0 ? ts->act[a.A_planes][0] : nullptr;
     t.A_lo = a.A_planes >= 0 ? ts->act[a.A_planes][1] : nullptr;
     t.A_elu = a.A_elu;
-    // Kernel choice by measurement (B200, 1024 images): the full tile (256 px x 128 ch per CTA) moves 4 KB of operands per
-    // 128x128x16 MMA from L2, the half-image tiles of k_conv_tc_h / k_conv_tc_p 5.3 KB -- and the convs are bound by exactly
-    // that (about 42 B/clk/SM of L2 -> SM delivery: 0.84 vs 0.87 ms for the 3x3, 1.95 vs 2.31 ms for the 5x5), so hiding the
-    // epilogue behind a TMEM ping-pong does not pay for the second weight fetch.  A 2-CTA cluster with multicast activation
-    // tiles (r1) measured no gain either (0.897 vs 0.880 ms) and is gone.  k_conv_tc_p stays selectable (bsw_set_conv_mode).
-    if (tc_persistent(c.ks <= 3 ? 1 : 2))
+    // Kernel choice by measurement (B200, 1024 images), see the mode mask above.  A 2-CTA cluster with multicast activation
+    // tiles but M = 128 MMAs (r1) measured no gain (0.897 vs 0.880 ms) and is gone; so is a pair kernel with N = 128 and a
+    // TMEM ping-pong (0.92 / 2.4 ms).
+    if (tc_persistent(c.ks <= 3 ? 8 : 16)) {
+        const int ntiles = (int)n;                                        // one pair tile per image
+        const unsigned pairs = tc_pgrid(ntiles * 2) / 2;                 // one cluster per SM pair, at most one per tile
+        k_conv_tc_2sm<<<2 * pairs, (2 + P2_NE) * 32, P2_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
+                                                                           s.map_hi, s.map_lo, t, ntiles);
+    } else if (tc_persistent(c.ks <= 3 ? 1 : 2))
         k_conv_tc_p<<<tc_pgrid((int)n * 4), TC_THREADS, P_SMEM_BYTES, st>>>(ts->act_map_h[a.in_planes][0], ts->act_map_h[a.in_planes][1],
                                                                            s.map_hi, s.map_lo, t, (int)n * 4);
     else

@@ -225,11 +225,13 @@ def test_p3_tc_single_layers(label, cfg):
 
 
 def test_p3_tc_persistent_kernel_equals_per_tile_kernels():
-    """k_conv_tc_p (one CTA per SM walking half-image tiles, TMEM ping-pong, default) against the per-tile grids
-    (k_conv_tc / k_conv_tc_h): same k-block and MMA order per accumulator, same epilogue arithmetic -> bit-identical mu and
-    sigma.  B = 80 gives 320 tiles per conv, i.e. up to three tiles per CTA: both accumulator buffers are reused and the
-    TMA ring runs across tile boundaries; every conv shape on the path (in-convs with 1 and 25 taps, dense 3x3, 5x5)."""
-    B = 80
+    """k_conv_tc_p (one CTA per SM walking half-image tiles, TMEM ping-pong) and k_conv_tc_2sm (2-CTA clusters issuing
+    cta_group::2 M = 256, N = 256 MMAs on one image per pair, epilogue out of shared memory under the next tile's MMAs;
+    the default for the dense convs) against the per-tile grids (k_conv_tc / k_conv_tc_h): same k-block and MMA order per
+    accumulator, same epilogue arithmetic -> bit-identical mu and sigma.  B = 170 gives 680 half-image tiles and 170 pair
+    tiles per conv, i.e. up to five tiles per CTA and three per pair: accumulators and the shared output tile are reused
+    and the TMA ring runs across tile boundaries; every conv shape on the path (in-convs with 1 and 25 taps, dense 3x3, 5x5)."""
+    B = 170
     cfg = CodecConfig(xs=(3, 32, 32), nz=2, zchannels=8, nprocessing=1, resdepth=1, reswidth=252)
     sd = synthetic.synthetic_state_dict(cfg, seed=61, varied=True)
     m = Model.from_config(cfg, max_batch=B, use_tensor_cores=True).load_state_dict(sd)
@@ -239,7 +241,7 @@ def test_p3_tc_persistent_kernel_equals_per_tile_kernels():
     gz = torch.from_numpy(rs.uniform(-5, 5, (B, cfg.zdim))).cuda()
     out = {}
     try:
-        for mode in (0, 7):
+        for mode in (0, 7, 24):                            # per-tile grids | persistent half-image tiles | cta_group::2 pair tiles
             check(lib().bsw_set_conv_mode(mode))
             res = []
             for i in range(cfg.nz):
@@ -251,8 +253,9 @@ def test_p3_tc_persistent_kernel_equals_per_tile_kernels():
             out[mode] = res
     finally:
         check(lib().bsw_set_conv_mode(-1))
-    for a, b in zip(out[0], out[7]):
-        assert torch.equal(a, b)
+    for mode in (7, 24):
+        for a, b in zip(out[0], out[mode]):
+            assert torch.equal(a, b), f"conv mode {mode}"
     assert all(torch.isfinite(t).all() for t in out[7])
 
 
