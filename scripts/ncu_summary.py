@@ -74,7 +74,7 @@ def full(path, out):
 
 # category, kernel-name regex, grid_dim_x of the launch (k_rows6: rows / 8 -> 256 for a 2048-row z level, 384 for the 3072-row x level)
 CATS = [("rows_z", r"k_rows6<", 256), ("rows_x", r"k_rows6<", 384), ("pop_z", r"k_pop6", None),
-        ("push_z", r"k_push_pairs", None), ("conv_dense3x3", r"k_conv_tc\(", "ms<1.3"), ("conv_dense5x5", r"k_conv_tc\(", "ms>=1.3"),
+        ("push_z", r"k_push_pairs", None), ("conv_dense3x3", r"k_conv_tc(_2sm)?\(", "ms<1.1"), ("conv_dense5x5", r"k_conv_tc(_2sm)?\(", "ms>=1.1"),
         ("conv_head", r"k_conv_tc_head", None), ("conv_in", r"k_conv_tc_h", None)]
 
 
