@@ -182,10 +182,10 @@ int bsw_rows6_set_verify(int on);
 /* Mapping of the affine-row table kernel: lanes of a warp that share one row (2, 4, 8 or 32; 0 = default 4, i.e. eight
  * rows per warp).  Every setting emits the same integers; exposed for A/B timing and the parity test. */
 int bsw_rows6_set_lanes_per_row(int lpr);
-/* Launch shape of the tcgen05 convolutions, a bit mask: 1 / 2 / 4 = dense 3x3 / dense 5x5 / in-convs on the persistent
- * kernel (one CTA per SM walking half-image tiles with a TMEM ping-pong), 8 / 16 = dense 3x3 / dense 5x5 on the pair-tile
- * kernel (2-CTA clusters, cta_group::2 MMAs on (image, 128 channels) tiles, TMEM ping-pong); unset = one CTA per tile.
- * -1 = default (BSW_TC_PERSIST or the built-in choice).  Bit-identical results. */
+/* Launch shape of the tcgen05 convolutions, a bit mask: 8 / 16 = dense 3x3 / dense 5x5 on the pair-tile kernel (2-CTA
+ * clusters issuing cta_group::2 M = 256, N = 256 MMAs, one image per pair, weight tile split across the pair), 1 / 2 / 4 =
+ * dense 3x3 / dense 5x5 / in-convs on the persistent kernel (one CTA per SM walking half-image tiles with a TMEM
+ * ping-pong); a clear bit = one CTA per tile.  -1 = default (BSW_TC_PERSIST if set, else 24).  Bit-identical results. */
 int bsw_set_conv_mode(int mode);
 int bsw_rows6_verify_read(uint64_t *out4_host);
 int bsw_logistic_push_2p(bsw_streams *s, int first, int count, const float *mu_dev, int64_t mu_stream_stride,
