@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
     const int kend = min(ks0 + CPL * pl.m, pl.kh);
     uint32_t rsum = 0, lbest = 0, pre = 0, pv = 0, npre = 0;
     bool have_pv = false;
-    uint32_t bestv[4] = {0u, 0u, 0u, 0u};
+    __shared__ uint4 bestq[512];                          // per thread: the four values of its best group so far (one predicated
+    uint32_t bq_addr;                                     // 16-byte store per update instead of four moves); volatile: not re-derived per store
+    asm volatile("{\n.reg .u64 t;\ncvta.to.shared.u64 t, %1;\ncvt.u32.u64 %0, t;\n}" : "=r"(bq_addr) : "l"(&bestq[threadIdx.x]));
     int bestk = ks0;
     uint32_t cpre[CPL];                                   // P-sum of my bins before chunk i (for the chunk bases of the pop side)
 #pragma unroll
@@ -132,12 +134,13 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
     if (ks0 < kend) {
         const double rho1 = r6_exp_neg(pl.dt), rho4 = r6_exp_neg(__dmul_rn(4.0, pl.dt));
         // four registers that just hold `zero` (a kernel argument, so the compiler cannot fold it), see r6_rcp_seed_lo
-        const int zlo[4] = {zero, zero + zero, zero * 3, zero * 5};
+        const int zlo[4] = {zero, zero, zero, zero};
         double ub = r6_exp_neg(__fma_rn((double)(ks0 - 1), pl.dt, pl.t0));       // exp(-t) at the endpoint below my first bin
         double Tprev = ks0 == 0 ? R6_MAGIC0 : r6_quant(ub, rmult2);             // lower edge of bin 0 is cdf = 0 (:184)
         int next_chunk = ks0, ci = 0;
-#pragma unroll 2
-        for (int k0 = ks0; k0 < kend; k0 += 4) {
+        // one 4-bin group; `last`: the group that ends the row, whose upper edge is cdf = 1 exactly (:184) -- peeled out of the
+        // loop below so that the loop does not carry the test and the two selects
+        auto group = [&](const int k0, const bool last) __attribute__((always_inline)) {
             if (POP && k0 == next_chunk) {                // chunk boundary: remember the P-sum so far
                 const uint32_t sofar = rsum + (uint32_t)(k0 - ks0);
 #pragma unroll
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
                 ++ci; next_chunk += pl.m;
             }
             uint32_t dlo[4], dhi[4], vv[4];
-            r6_group_q(ub, Tprev, rho1, rho4, rmult2, Tone, k0 + 4 == S, zlo, pl.win, dlo, dhi);
+            r6_group_q(ub, Tprev, rho1, rho4, rmult2, Tone, last, zlo, pl.win, dlo, dhi);
             bool any = false;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -185,14 +188,12 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
             rsum += gsum;
             if (gmax > lbest) {                           // strict: the earlier group keeps a tie (:35 first maximum)
                 lbest = gmax; bestk = k0;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) bestv[t] = vv[t];
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(bq_addr), "r"(vv[0]), "r"(vv[1]), "r"(vv[2]), "r"(vv[3]) : "memory");
             }
-            if (!POP) {                                   // sy differs between the rows of a warp: selects, and one rare branch per row
-                const bool below = k0 + 4 <= sy;
-                pre += below ? gsum : 0u;
-                npre += below ? 4u : 0u;
-                if (!below && k0 <= sy) {
+            if (!POP) {                                   // the group that holds my row's symbol: once per row, in one of its lanes
+                if ((unsigned)(sy - k0) < 4u) {
+                    pre = rsum - gsum;                    // my bins before this group (rsum already holds the group)
+                    npre = (uint32_t)(k0 - ks0);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         if (k0 + t < sy) { pre += vv[t]; ++npre; }
@@ -200,7 +201,12 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
                     }
                 }
             }
-        }
+        };
+        const int kmain = kend == S ? kend - 4 : kend;
+#pragma unroll 2
+        for (int k0 = ks0; k0 < kmain; k0 += 4) group(k0, false);
+        if (kend == S) group(kend - 4, true);
+        if (!POP && sy >= kend) { pre = rsum; npre = (uint32_t)(kend - ks0); }      // all my bins lie below the symbol
         if (POP) {                                        // chunks past my last bin: the P-sum of all my bins
             const uint32_t sofar = rsum + (uint32_t)(kend - ks0);
 #pragma unroll
@@ -209,8 +215,13 @@ __global__ void __launch_bounds__(512, 2) k_rows6(int count, int64_t L, int S, c
     }
     const uint32_t nbin = ks0 < kend ? (uint32_t)(kend - ks0) : 0u;
     int lbi = bestk;                                      // first position of the maximum inside its group
+    if (lbest) {                                          // (no group beat the initial 0: every value is 0, the first bin stands)
+        uint4 bq;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(bq.x), "=r"(bq.y), "=r"(bq.z), "=r"(bq.w) : "r"(bq_addr) : "memory");
+        const uint32_t bestv[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-    for (int t = 3; t >= 0; --t) if (bestv[t] == lbest) lbi = bestk + t;
+        for (int t = 3; t >= 0; --t) if (bestv[t] == lbest) lbi = bestk + t;
+    }
     // back to P = trunc + 1
     const uint32_t lsum = rsum + nbin;
     pre += npre;
